@@ -1,0 +1,217 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (nordmtr/quantpy).
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python tools/make_golden.py
+
+The reference imports ``cvxopt`` at module scope (quantpy/tomography/interval.py:6) and
+cvxopt is not installed here, so a stub module is registered first; nothing on the
+state/process bootstrap path touches it.  Every array stored below is an OUTPUT OF THE
+REFERENCE for the stored inputs; the tests compare the oracle and the CUDA path to them.
+"""
+
+import json
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def load_reference():
+    if "cvxopt" not in sys.modules:
+        stub = types.ModuleType("cvxopt")
+
+        class _Solvers:
+            options = {}
+
+        stub.matrix = lambda *a, **k: None
+        stub.solvers = _Solvers()
+        sys.modules["cvxopt"] = stub
+    sys.path.insert(0, REF)
+    import quantpy  # noqa: E402
+
+    return quantpy
+
+
+def haar_mixed(n, rng, rank=None):
+    d = 2**n
+    k = d if rank is None else rank
+    g = rng.normal(size=(d, k)) + 1j * rng.normal(size=(d, k))
+    rho = g @ g.conj().T
+    return rho / np.trace(rho)
+
+
+def state_case(qp, n, povm, n_shots, seed, n_samples, rank=None, with_mle=True, mle_tight=False):
+    rng = np.random.default_rng(seed)
+    rho = haar_mixed(n, rng, rank)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(seed)
+    out = {"rho_true": rho, "n_qubits": n, "povm_name": povm, "seed": seed}
+    counts, lin_phys, lin_raw, mle_def, mle_tightv, n_meas = [], [], [], [], [], None
+    d_hs, d_tr, d_if = [], [], []
+    for _ in range(n_samples):
+        tmg.experiment(n_shots, povm)
+        counts.append(tmg.results.copy())
+        n_meas = np.asarray(tmg.n_measurements, dtype=float)
+        lp = tmg.point_estimate("lin", physical=True).matrix
+        lr = tmg.point_estimate("lin", physical=False).matrix
+        lin_phys.append(lp)
+        lin_raw.append(lr)
+        d_hs.append(float(qp.hs_dst(lp, rho)))
+        d_tr.append(float(qp.trace_dst(lp, rho)))
+        d_if.append(float(qp.if_dst(lp, rho)))
+        if with_mle:
+            mle_def.append(tmg.point_estimate("mle").matrix)
+        if mle_tight:
+            mle_tightv.append(tmg.point_estimate("mle", tol=1e-12, max_iter=100000).matrix)
+    out.update(
+        povm_matrix=tmg.povm_matrix, n_meas=n_meas, counts=np.array(counts),
+        lin_physical=np.array(lin_phys), lin_raw=np.array(lin_raw),
+        dist_hs=np.array(d_hs), dist_trace=np.array(d_tr), dist_if=np.array(d_if),
+        probs=np.clip(np.einsum("ijk,k->ij", tmg.povm_matrix, tmg.state.bloch) * 2**n, 0, 1),
+    )
+    if with_mle:
+        out["mle_default"] = np.array(mle_def)
+    if mle_tight:
+        out["mle_tight"] = np.array(mle_tightv)
+    return out
+
+
+def bootstrap_case(qp, n, povm, n_shots, seed, n_points, method):
+    rng = np.random.default_rng(seed)
+    rho = haar_mixed(n, rng)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(seed)
+    tmg.experiment(n_shots, povm)
+    first_counts = tmg.results.copy()
+    centre = tmg.point_estimate("lin").matrix
+    itv = qp.BootstrapStateInterval(tmg, n_points=n_points, method=method)
+    np.random.seed(seed + 1)
+    dist, cl = itv(np.array([0.0, 0.1, 0.5, 0.9, 0.95, 1.0]))
+    xs = itv.cl_to_dist.x
+    ys = itv.cl_to_dist.y
+    return dict(rho_true=rho, counts=first_counts, centre=centre, povm_matrix=tmg.povm_matrix,
+                n_meas=np.asarray(tmg.n_measurements, float), sorted_dist=ys, grid=xs,
+                query_cl=cl, query_dist=dist, seed=seed, n_points=n_points)
+
+
+def process_cases(qp):
+    out = {}
+    # --- the only known-input run the reference ships: input.json + scripts/process_interval.py --no-ci
+    with open(os.path.join(REF, "input.json")) as fp:
+        data = json.load(fp)
+    results = np.asarray(data["outcomes"])
+    povm = np.asarray(data["povm_matrix"])
+    inputs = [qp.Qobj(b) for b in data["input_states"]]
+    tmg = qp.ProcessTomograph(qp.channel.depolarizing(n_qubits=1), input_states=inputs)
+    np.random.seed(0)
+    tmg.experiment(1000, "proj-set")
+    tmg.results = results
+    ch = tmg.point_estimate(cptp=False)
+    out["json_outcomes"] = results
+    out["json_povm"] = povm
+    out["json_inputs"] = np.array([q.matrix for q in inputs])
+    out["json_choi_bloch"] = np.asarray(ch.choi.bloch)
+    out["json_choi"] = np.asarray(ch.choi.matrix)
+    out["json_choi_cptp"] = np.asarray(tmg.point_estimate(cptp=True).choi.matrix)
+    # --- depolarising channel, 1 and 2 qubits, sic inputs
+    for n, nrep in ((1, 4), (2, 2)):
+        chan = qp.channel.depolarizing(p=0.1, n_qubits=n)
+        tmg = qp.ProcessTomograph(chan, input_states="sic")
+        np.random.seed(10 + n)
+        counts, raw, proj, sts, d_hs = [], [], [], [], []
+        for _ in range(nrep):
+            tmg.experiment(10000, "proj-set")
+            counts.append(tmg.results.copy())
+            raw.append(tmg.point_estimate("lifp", cptp=False).choi.matrix)
+            est = tmg.point_estimate("lifp", cptp=True)
+            proj.append(est.choi.matrix)
+            d_hs.append(float(qp.hs_dst(est.choi, chan.choi)))
+            sts.append(tmg.point_estimate("states", cptp=True).choi.matrix)
+        out[f"dep{n}_choi_true"] = np.asarray(chan.choi.matrix)
+        out[f"dep{n}_inputs"] = np.array([q.matrix for q in tmg.input_basis.elements])
+        out[f"dep{n}_outputs"] = np.array([t.state.matrix for t in tmg.tomographs])
+        out[f"dep{n}_povm"] = tmg.tomographs[0].povm_matrix
+        out[f"dep{n}_n_meas"] = np.asarray(tmg.tomographs[0].n_measurements, float)
+        out[f"dep{n}_counts"] = np.array(counts)
+        out[f"dep{n}_lifp_raw"] = np.array(raw)
+        out[f"dep{n}_lifp_cptp"] = np.array(proj)
+        out[f"dep{n}_states_cptp"] = np.array(sts)
+        out[f"dep{n}_dist_hs"] = np.array(d_hs)
+    # --- 1-qubit process bootstrap with the legacy RNG stream
+    chan = qp.channel.depolarizing(p=0.1, n_qubits=1)
+    tmg = qp.ProcessTomograph(chan, input_states="sic")
+    np.random.seed(21)
+    tmg.experiment(10000, "proj-set")
+    tmg.point_estimate("lifp", cptp=True)
+    itv = qp.BootstrapProcessInterval(tmg, n_points=12)
+    np.random.seed(22)
+    itv.setup()
+    out["boot1_counts"] = tmg.results.copy()
+    out["boot1_centre"] = np.asarray(tmg.reconstructed_channel.choi.matrix)
+    out["boot1_sorted_dist"] = itv.cl_to_dist.y
+    return out
+
+
+def api_cases(qp):
+    out = {}
+    for name in ("proj", "proj-set", "proj4", "sic"):
+        for n in (1, 2):
+            out[f"povm_{name}_{n}"] = qp.generate_measurement_matrix(name, n)
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3):
+        rho = haar_mixed(n, rng)
+        out[f"rho_{n}"] = rho
+        out[f"bloch_{n}"] = qp.Qobj(rho).bloch
+        out[f"back_{n}"] = qp.Qobj(qp.Qobj(rho).bloch).matrix
+    rho2 = out["rho_2"]
+    out["ptrace_keep0"] = qp.Qobj(rho2).ptrace([0]).matrix
+    out["ptrace_keep1"] = qp.Qobj(rho2).ptrace([1]).matrix
+    chan = qp.channel.depolarizing(p=0.3, n_qubits=1)
+    out["dep03_choi"] = chan.choi.matrix
+    out["dep03_apply"] = qp.Channel(chan.choi.matrix).transform(qp.Qobj(out["rho_1"])).matrix
+    out["zchan_choi"] = qp.operator.Z.as_channel().choi.matrix
+    out["ket01_bloch"] = qp.Qobj([0, 1], is_ket=True).bloch
+    basis = qp.basis.Basis([qp.Qobj(b) for b in np.squeeze(qp.generate_measurement_matrix("sic", 1))])
+    out["basis_gram"] = basis.gram
+    out["basis_decomp"] = basis.decompose(qp.Qobj(out["rho_1"]))
+    a, b = haar_mixed(2, rng), haar_mixed(2, rng)
+    out["dst_a"], out["dst_b"] = a, b
+    out["dst_vals"] = np.array([qp.hs_dst(a, b), qp.trace_dst(a, b), qp.if_dst(a, b)], dtype=float)
+    return out
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    os.makedirs(OUT, exist_ok=True)
+    qp = load_reference()
+    cases = {
+        "state_c1": state_case(qp, 1, "proj-set", 10000, 1, 6, mle_tight=True),
+        "state_c1_pure": state_case(qp, 1, "proj-set", 10000, 2, 4, rank=1, mle_tight=True),
+        "state_c2": state_case(qp, 2, "proj", 10000, 3, 6, mle_tight=True),
+        "state_c2_set": state_case(qp, 2, "proj-set", 10000, 4, 4),
+        "state_c2_rank1": state_case(qp, 2, "proj", 10000, 5, 4, rank=1),
+        "state_c2_sic": state_case(qp, 2, "sic", 10000, 6, 4),
+        "state_c3": state_case(qp, 3, "proj", 10000, 7, 3, with_mle=False),
+        "state_c3_rank2": state_case(qp, 3, "proj", 10000, 8, 3, rank=2, with_mle=False),
+        "state_c4": state_case(qp, 4, "proj", 10000, 9, 2, with_mle=False),
+        "boot_c1_lin": bootstrap_case(qp, 1, "proj-set", 10000, 31, 40, "lin"),
+        "boot_c2_lin": bootstrap_case(qp, 2, "proj", 10000, 32, 25, "lin"),
+        "boot_c1_mle": bootstrap_case(qp, 1, "proj-set", 10000, 33, 10, "mle"),
+        "process": process_cases(qp),
+        "api": api_cases(qp),
+    }
+    for name, arrays in cases.items():
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **arrays)
+        print(f"{name}: {os.path.getsize(path)} bytes")
+
+
+if __name__ == "__main__":
+    main()
