@@ -1,0 +1,119 @@
+/*
+ * quantpy_b200 C ABI -- B200 (sm_100a) kernels for the tomography-bootstrap hot path of
+ * nordmtr/quantpy.  The reference has no FFI; its boundary is a Python class API
+ * (quantpy/__init__.py:1-23).  Each entry point below replaces the per-sample arithmetic of one
+ * reference method; the Python package quantpy_b200 binds them with ctypes (INTEGRATION.md shows
+ * the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer unless its name ends in _host.  The caller owns all
+ *    buffers.  `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *    asynchronous with respect to the host.
+ *  - Return value: 0 on success, negative on error (QPB_ERR_*); qpb_last_error() gives the
+ *    message for the calling thread.  No exceptions cross the ABI.  Thread-compatible.
+ *  - Reference conventions are kept at the boundary: POVM rows and states are real Bloch
+ *    (Pauli-coefficient) vectors in the reference's Pauli order (quantpy/routines.py:14-19),
+ *    density/Choi matrices are row-major complex128 (re,im pairs), Choi vectorisation is column
+ *    stacking (quantpy/routines.py:53-61).  Counts are int32 (the reference's int64 counts are
+ *    narrowed by the Python layer; shots per POVM must be < 2^31).
+ *  - n = number of qubits (1..4), d = 2^n, D = 4^n, P POVMs of O outcomes, K = P*O, B = batch.
+ */
+#ifndef QUANTPY_B200_H
+#define QUANTPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPB_ABI_VERSION 1
+#if defined(__GNUC__)
+#define QPB_API __attribute__((visibility("default")))
+#else
+#define QPB_API
+#endif
+
+enum { QPB_DIST_HS = 0, QPB_DIST_TRACE = 1, QPB_DIST_IF = 2 };       /* quantpy/geometry.py:5-56 */
+enum { QPB_METHOD_LIN = 0, QPB_METHOD_MLE = 1 };                     /* state.py:143-189 */
+enum { QPB_INIT_LIN = 0, QPB_INIT_MIXED = 1 };                       /* state.py:206-211 */
+
+QPB_API int qpb_abi_version(void);
+QPB_API const char* qpb_last_error(void);
+/* Number of kernels launched by this library since load / since the last reset (bench bookkeeping). */
+QPB_API int64_t qpb_launch_count(void);
+QPB_API void qpb_reset_launch_count(void);
+
+/* ---- state plan ---------------------------------------------------------------------------
+ * Device-resident operator tables for one (POVM, shot vector) pair, hoisted out of the
+ * per-sample loop.  Inputs are exactly the reference's intermediates:
+ *   A [K,D]  shot-weighted POVM rows  povm_matrix*n_m/sum(n)        (state.py:193-196, 221-224)
+ *   L [D,K]  _left_inv(A) = (A^T A)^-1 A^T                           (routines.py:69-71); may be
+ *            NULL if neither 'lin' nor init='lin' is used.
+ * The plan converts both to the packed-Hermitian basis on the device.                         */
+typedef struct qpb_state_plan qpb_state_plan;
+QPB_API int qpb_state_plan_create(qpb_state_plan** plan, int n_qubits, int K, const double* A, const double* L,
+                          void* stream);
+QPB_API int qpb_state_plan_destroy(qpb_state_plan* plan);
+
+/* k1: p[b,k] = scale * sum_i M[k,i] r[b,i], optionally clipped to [0,1].
+ * Replaces np.einsum("ijk,k->ij", povm_matrix, bloch)*2^n + np.clip (state.py:109-110).        */
+QPB_API int qpb_povm_probs(int K, int D, int B, const double* M, const double* r, double scale, int clip,
+                   double* p, void* stream);
+
+/* k2: counts[b,m,:] ~ Multinomial(n_shots[m], p[m,:]) for b in [0,B), Philox4x32-10 keyed by
+ * (seed, offset+b, m): the draw for a global sample index does not depend on B or on how
+ * samples are split across GPUs.  Like np.random.multinomial (state.py:111-114) the last outcome
+ * takes the remaining probability mass and sum_o counts[b,m,o] == n_shots[m] exactly.
+ * p is [P,O] (p_batched=0, shared by all b) or [B,P,O] (p_batched=1).  n_shots_host is a HOST array. */
+QPB_API int qpb_multinomial(int B, int P, int O, const double* p, int p_batched, const int32_t* n_shots_host,
+                    uint64_t seed, uint64_t offset, int32_t* counts, void* stream);
+
+/* k3-k5: linear inversion + optional projection onto physical states.
+ * Replaces StateTomograph._point_estimate_lin + _make_feasible (state.py:191-202, 267-273).
+ * counts [B,K] -> rho [B,d,d] complex128.                                                       */
+QPB_API int qpb_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts, int physical, double* rho,
+                    void* stream);
+
+/* Fused iterative maximum likelihood rho <- R rho R / Tr(R rho R), R = sum_k f_k/(p_k+1e-10) E_k,
+ * stopping per batch element when ||rho' - rho||_F < tol or after max_iter iterations.
+ * Stands where the reference runs SciPy BFGS over a Cholesky factor (state.py:204-229); see
+ * DESIGN.md for why the update differs (BASELINE.json north_star) and how parity is defined.
+ * rho0 [B,d,d] start states (NULL = maximally mixed).  rho [B,d,d] out, iters [B] out (may be NULL). */
+QPB_API int qpb_mle_rrr(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
+                double tol, double* rho, int32_t* iters, void* stream);
+
+/* k8: dist[b] = dst(rho[b], ref) with the reference's argument order dst(estimate, centre)
+ * (interval.py:609) and its "below 1e-15 -> 0" rule.  dd is the matrix side (d or d^2 for Choi). */
+QPB_API int qpb_distance(int dd, int B, const double* rho, const double* ref, int kind, double* dist, void* stream);
+
+/* Fused bootstrap of interval.py:598-609: for each b sample counts from probs [P,O], reconstruct
+ * with `method`, and measure the distance to `ref` [d,d].  Outputs dist [B]; rho_out [B,d,d],
+ * counts_out [B,K], iters_out [B] are optional (NULL) -- counts_out doubles as workspace and is
+ * required unless the library can fuse the sampler (it cannot yet).  work is a caller-owned
+ * scratch buffer of qpb_bootstrap_state_workspace(...) bytes.                                   */
+QPB_API size_t qpb_bootstrap_state_workspace(const qpb_state_plan* plan, int B, int P, int O);
+QPB_API int qpb_bootstrap_state(const qpb_state_plan* plan, int B, int P, int O, const double* probs,
+                        const int32_t* n_shots_host, uint64_t seed, uint64_t offset, int method, int physical,
+                        int init, int max_iter, double tol, const double* ref, int dist_kind, double* dist,
+                        double* rho_out, int32_t* counts_out, int32_t* iters_out, void* work, void* stream);
+
+/* ---- process path -------------------------------------------------------------------------
+ * Linv [d^4, S*K] complex128 = _left_inv(_lifp_oper) (process.py:197-209, plain transpose).
+ * counts [B,S,K]; frequencies are normalised per input state (process.py:285).
+ * choi [B,d^2,d^2] complex128 out; if cptp!=0 the alternating TP/CP projection of
+ * process.py:237-278 runs for at most n_iter iterations with stop value tol; iters [B] optional. */
+typedef struct qpb_process_plan qpb_process_plan;
+QPB_API int qpb_process_plan_create(qpb_process_plan** plan, int n_qubits, int S, int K, const double* Linv,
+                            void* stream);
+QPB_API int qpb_process_plan_destroy(qpb_process_plan* plan);
+QPB_API int qpb_lifp_cptp(const qpb_process_plan* plan, int B, const int32_t* counts, int cptp, int n_iter, double tol,
+                  double* choi, int32_t* iters, void* stream);
+/* CPTP projection alone (process.py:231-257) on a batch of Choi matrices, in place allowed. */
+QPB_API int qpb_cptp_project(int n_qubits, int B, const double* choi_in, int n_iter, double tol, double* choi_out,
+                     int32_t* iters, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUANTPY_B200_H */

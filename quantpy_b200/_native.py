@@ -1,0 +1,119 @@
+"""ctypes binding of libquantpy_b200.so (include/quantpy_b200.h).
+
+PyTorch is used only for plumbing: device memory (tensors), the current CUDA stream and
+torch.distributed.  There is NO CPU fallback: every entry point raises if the shared library or
+a CUDA device is missing.
+"""
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libquantpy_b200.so")
+
+DIST_KINDS = {"hs": 0, "trace": 1, "if": 2}
+METHODS = {"lin": 0, "mle": 1}
+INITS = {"lin": 0, "mixed": 1}
+
+_lib = None
+_lock = threading.Lock()
+
+c_i32p = ctypes.c_void_p
+_vp = ctypes.c_void_p
+_int = ctypes.c_int
+_dbl = ctypes.c_double
+_u64 = ctypes.c_uint64
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "qpb_abi_version": (_int, []),
+    "qpb_last_error": (ctypes.c_char_p, []),
+    "qpb_launch_count": (ctypes.c_int64, []),
+    "qpb_reset_launch_count": (None, []),
+    "qpb_state_plan_create": (_int, [ctypes.POINTER(_vp), _int, _int, _vp, _vp, _vp]),
+    "qpb_state_plan_destroy": (_int, [_vp]),
+    "qpb_povm_probs": (_int, [_int, _int, _int, _vp, _vp, _dbl, _int, _vp, _vp]),
+    "qpb_multinomial": (_int, [_int, _int, _int, _vp, _int, _vp, _u64, _u64, _vp, _vp]),
+    "qpb_lin_project": (_int, [_vp, _int, _vp, _int, _vp, _vp]),
+    "qpb_mle_rrr": (_int, [_vp, _int, _vp, _vp, _int, _dbl, _vp, _vp, _vp]),
+    "qpb_distance": (_int, [_int, _int, _vp, _vp, _int, _vp, _vp]),
+    "qpb_bootstrap_state_workspace": (ctypes.c_size_t, [_vp, _int, _int, _int]),
+    "qpb_bootstrap_state": (_int, [_vp, _int, _int, _int, _vp, _vp, _u64, _u64, _int, _int, _int, _int, _dbl,
+                                   _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qpb_process_plan_create": (_int, [ctypes.POINTER(_vp), _int, _int, _int, _vp, _vp]),
+    "qpb_process_plan_destroy": (_int, [_vp]),
+    "qpb_lifp_cptp": (_int, [_vp, _int, _vp, _int, _int, _dbl, _vp, _vp, _vp]),
+    "qpb_cptp_project": (_int, [_int, _int, _vp, _int, _dbl, _vp, _vp, _vp]),
+}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load the shared library (no GPU needed).  Raises NativeError if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeError(
+                    f"{LIB_PATH} is missing: build it with `make -C quantpy_b200/csrc` "
+                    "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+                    "quantpy_b200 has no CPU fallback."
+                )
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            if lib.qpb_abi_version() != 1:
+                raise NativeError("libquantpy_b200.so ABI version mismatch")
+            _lib = lib
+    return _lib
+
+
+def torch_cuda():
+    """Return the torch module after checking that a CUDA device is usable."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise NativeError("quantpy_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch
+
+
+def check(rc):
+    if rc != 0:
+        msg = load_library().qpb_last_error()
+        raise NativeError(f"libquantpy_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def stream_ptr():
+    torch = torch_cuda()
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def to_device(array, dtype):
+    """Host array -> contiguous device tensor of the given torch dtype."""
+    torch = torch_cuda()
+    a = np.ascontiguousarray(array)
+    return torch.from_numpy(a).to(device="cuda", dtype=dtype, non_blocking=False).contiguous()
+
+
+def complex_to_host(t):
+    """Device float64 tensor [..., 2] of (re, im) pairs -> complex128 numpy array."""
+    return np.ascontiguousarray(t.cpu().numpy()).view(np.complex128)[..., 0]
+
+
+def complex_to_device(array):
+    """complex numpy array -> device float64 tensor with a trailing (re, im) axis."""
+    torch = torch_cuda()
+    a = np.ascontiguousarray(np.asarray(array, dtype=np.complex128))
+    return torch.from_numpy(a.view(np.float64).reshape(a.shape + (2,))).cuda()

@@ -1,0 +1,136 @@
+// Warp-cooperative cyclic Jacobi eigensolver for small complex Hermitian matrices held in
+// shared memory (d = 2, 4, 8, 16).  Replaces the LAPACK zheevr calls behind scipy.linalg.eigh at
+// quantpy/tomography/state.py:270 and quantpy/tomography/process.py:273.
+//
+// One warp owns one matrix.  A sweep is d-1 rounds of a round-robin tournament; the d/2 pairs of
+// a round are disjoint, so their rotations are computed from the same matrix and applied together
+// (columns, then rows, then the eigenvector accumulator).
+#pragma once
+#include "common.cuh"
+
+namespace qpb {
+
+struct jrot {
+    double c, s, ur, ui;  // G = [[c, s*u], [-s*conj(u), c]],  u = A_pq / |A_pq|
+    int p, q;
+};
+
+__device__ __forceinline__ void jacobi_pair(int d, int round, int i, int& p, int& q) {
+    const int m = d - 1;
+    int a, b;
+    if (i == 0) {
+        a = m;
+        b = round;
+    } else {
+        a = (round + i) % m;
+        b = (round - i + m) % m;
+    }
+    p = a < b ? a : b;
+    q = a < b ? b : a;
+}
+
+// A: d*d row-major complex Hermitian (destroyed: diagonal holds eigenvalues on return).
+// V: d*d row-major; on return column j is the eigenvector of eigenvalue A[j][j].  If !WANT_V, V unused.
+// rot: d/2 jrot entries of scratch.  All pointers are shared memory private to this warp.
+template <bool WANT_V>
+__device__ void warp_jacobi(cplx* __restrict__ A, cplx* __restrict__ V, jrot* __restrict__ rot, int d, int lane) {
+    const int dd = d * d;
+    const int half = d >> 1;
+    if (WANT_V) {
+        for (int e = lane; e < dd; e += 32) {
+            V[e].re = (e / d == e % d) ? 1.0 : 0.0;
+            V[e].im = 0.0;
+        }
+    }
+    __syncwarp();
+    for (int sweep = 0; sweep < 40; ++sweep) {
+        double off = 0.0, fro = 0.0;
+        for (int e = lane; e < dd; e += 32) {
+            double m2 = A[e].re * A[e].re + A[e].im * A[e].im;
+            fro += m2;
+            if (e / d != e % d) off += m2;
+        }
+        off = warp_sum(off);
+        fro = warp_sum(fro);
+        if (off <= 1e-33 * fro || fro == 0.0) break;
+        const double tiny2 = 1e-40 * fro;
+        for (int round = 0; round < d - 1; ++round) {
+            if (lane < half) {
+                int p, q;
+                jacobi_pair(d, round, lane, p, q);
+                double al = A[p * d + p].re, ga = A[q * d + q].re;
+                double br = A[p * d + q].re, bi = A[p * d + q].im;
+                double b2 = br * br + bi * bi;
+                jrot r;
+                r.p = p;
+                r.q = q;
+                if (b2 <= tiny2) {
+                    r.c = 1.0; r.s = 0.0; r.ur = 1.0; r.ui = 0.0;
+                } else {
+                    double ab = sqrt(b2);
+                    double tau = (ga - al) / (2.0 * ab);
+                    double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                    r.c = 1.0 / sqrt(1.0 + t * t);
+                    r.s = t * r.c;
+                    r.ur = br / ab;
+                    r.ui = bi / ab;
+                }
+                rot[lane] = r;
+            }
+            __syncwarp();
+            // columns: A <- A G  (and V <- V G)
+            for (int w = lane; w < half * d; w += 32) {
+                const jrot r = rot[w / d];
+                const int row = w % d;
+                cplx x = A[row * d + r.p], y = A[row * d + r.q];
+                // su = s*u ; A'_rp = c x - s conj(u) y ; A'_rq = s u x + c y
+                double sur = r.s * r.ur, sui = r.s * r.ui;
+                cplx nx, ny;
+                nx.re = r.c * x.re - (sur * y.re + sui * y.im);
+                nx.im = r.c * x.im - (sur * y.im - sui * y.re);
+                ny.re = (sur * x.re - sui * x.im) + r.c * y.re;
+                ny.im = (sur * x.im + sui * x.re) + r.c * y.im;
+                A[row * d + r.p] = nx;
+                A[row * d + r.q] = ny;
+                if (WANT_V) {
+                    cplx vx = V[row * d + r.p], vy = V[row * d + r.q];
+                    cplx mx, my;
+                    mx.re = r.c * vx.re - (sur * vy.re + sui * vy.im);
+                    mx.im = r.c * vx.im - (sur * vy.im - sui * vy.re);
+                    my.re = (sur * vx.re - sui * vx.im) + r.c * vy.re;
+                    my.im = (sur * vx.im + sui * vx.re) + r.c * vy.im;
+                    V[row * d + r.p] = mx;
+                    V[row * d + r.q] = my;
+                }
+            }
+            __syncwarp();
+            // rows: A <- G^dagger A :  A'_p. = c A_p. - s u A_q. ;  A'_q. = s conj(u) A_p. + c A_q.
+            for (int w = lane; w < half * d; w += 32) {
+                const jrot r = rot[w / d];
+                const int col = w % d;
+                cplx x = A[r.p * d + col], y = A[r.q * d + col];
+                double sur = r.s * r.ur, sui = r.s * r.ui;
+                cplx nx, ny;
+                nx.re = r.c * x.re - (sur * y.re - sui * y.im);
+                nx.im = r.c * x.im - (sur * y.im + sui * y.re);
+                ny.re = (sur * x.re + sui * x.im) + r.c * y.re;
+                ny.im = (sur * x.im - sui * x.re) + r.c * y.im;
+                A[r.p * d + col] = nx;
+                A[r.q * d + col] = ny;
+            }
+            __syncwarp();
+            if (lane < half) {
+                const jrot r = rot[lane];
+                if (r.s != 0.0) {
+                    A[r.p * d + r.q].re = 0.0; A[r.p * d + r.q].im = 0.0;
+                    A[r.q * d + r.p].re = 0.0; A[r.q * d + r.p].im = 0.0;
+                }
+                A[r.p * d + r.p].im = 0.0;
+                A[r.q * d + r.q].im = 0.0;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace qpb

@@ -1,0 +1,31 @@
+// Internal plan structures and cross-file launch helpers (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct qpb_state_plan {
+    int n = 0, d = 0, D = 0, K = 0;
+    double* Ar = nullptr;   // [K][D] packed-Hermitian POVM operators
+    double* ArT = nullptr;  // [D][K]
+    double* LhT = nullptr;  // [K][D] packed-Hermitian linear-inversion map (NULL if no L given)
+};
+
+struct qpb_process_plan {
+    int n = 0, d = 0, S = 0, K = 0;
+    int d4 = 0;              // d^4 = number of Choi entries
+    double* LinvT = nullptr;  // [S*K][2*d4] : (re, im) of Linv[:, col] per input column, row-major Choi
+};
+
+namespace qpb {
+
+int launch_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts, int physical, double* rho,
+                       cudaStream_t st);
+int launch_mle_generic(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
+                       double tol, double* rho, int32_t* iters, cudaStream_t st);
+int launch_distance(int d, int B, const double* rho, const double* ref, int kind, double* dist, cudaStream_t st);
+// Specialised register-resident kernels for n <= 2 (mle_small.cu).  Returns QPB_ERR_UNSUPPORTED when
+// the shape has no specialisation, in which case the caller uses the generic kernel.
+int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
+                     double tol, double* rho, int32_t* iters, cudaStream_t st);
+
+}  // namespace qpb

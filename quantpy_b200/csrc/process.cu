@@ -1,0 +1,253 @@
+// Process-tomography kernels: 'lifp' linear inversion of the Choi matrix and the alternating
+// TP/CP projection of quantpy/tomography/process.py:231-289.
+//
+// Layout: Choi matrices are s x s complex128, s = d^2, row-major, row/column index (i,a) = i*d + a
+// with i the input and a the output factor (Choi = sum_ij E_ij (x) Phi(E_ij), channel.py:95-103).
+// LinvT [S*K][s*s][2] holds, for every measurement column, the (re,im) contribution to each Choi
+// entry (the column-stacking permutation of routines.py:53-61 is folded in at plan creation).
+#include "../../include/quantpy_b200.h"
+#include "common.cuh"
+#include "jacobi.cuh"
+#include "plan.h"
+
+namespace qpb {
+
+// LinvT[col][r*s + c] = Linv[(c*s + r)][col]   (vec index = column stacking)
+__global__ void k_lifp_prep(const double* __restrict__ Linv, int s, int cols, double* __restrict__ LinvT) {
+    const long ss = (long)s * s, total = ss * cols;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long col = t / ss, e = t % ss;
+        const int r = (int)(e / s), c = (int)(e % s);
+        const long src = ((long)c * s + r) * cols + col;
+        LinvT[2 * t] = Linv[2 * src];
+        LinvT[2 * t + 1] = Linv[2 * src + 1];
+    }
+}
+
+// choi[b] = sum_col LinvT[col] * freq[b][col];  freq normalised per input state (process.py:285).
+// One warp per sample; shared per warp: freq[S*K].
+__global__ void k_lifp(int S, int K, int ss, int B, const double* __restrict__ LinvT,
+                       const int32_t* __restrict__ counts, double* __restrict__ choi) {
+    extern __shared__ double smf[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int cols = S * K;
+    double* f = smf + (size_t)warp * cols;
+    for (long b = (long)blockIdx.x * nw + warp; b < B; b += (long)gridDim.x * nw) {
+        const int32_t* c = counts + b * cols;
+        for (int si = 0; si < S; ++si) {
+            long long tot = 0;
+            for (int k = lane; k < K; k += 32) tot += c[si * K + k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            const double total = (double)tot;
+            for (int k = lane; k < K; k += 32) f[si * K + k] = (double)c[si * K + k] / total;
+        }
+        __syncwarp();
+        double* out = choi + b * 2 * ss;
+        for (int e = lane; e < 2 * ss; e += 32) {
+            double acc = 0.0;
+            for (int col = 0; col < cols; ++col) acc += LinvT[(long)col * 2 * ss + e] * f[col];
+            out[e] = acc;
+        }
+        __syncwarp();
+    }
+}
+
+__host__ __device__ inline size_t cptp_smem_per_warp(int s) {
+    return sizeof(cplx) * 7 * (size_t)s * s + sizeof(jrot) * (size_t)(s / 2 + 1) + sizeof(cplx) * 16;
+}
+
+// Alternating projection of process.py:237-257, one warp per Choi matrix.
+__global__ void k_cptp(int d, int B, const double* __restrict__ choi_in, int n_iter, double tol,
+                       double* __restrict__ choi_out, int32_t* __restrict__ iters) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int s = d * d, ss = s * s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    unsigned char* base = smraw + (size_t)warp * cptp_smem_per_warp(s);
+    cplx* x = reinterpret_cast<cplx*>(base);
+    cplx* p = x + ss;
+    cplx* q = p + ss;
+    cplx* y = q + ss;
+    cplx* A = y + ss;
+    cplx* V = A + ss;
+    cplx* T = V + ss;
+    cplx* rin = T + ss;  // d*d <= 16
+    jrot* rot = reinterpret_cast<jrot*>(rin + 16);
+    const double invd = 1.0 / d;
+
+    for (long b = (long)blockIdx.x * nw + warp; b < B; b += (long)gridDim.x * nw) {
+        const cplx* src = reinterpret_cast<const cplx*>(choi_in) + b * ss;
+        for (int e = lane; e < ss; e += 32) {
+            x[e] = src[e];
+            p[e].re = p[e].im = 0.0;
+            q[e].re = q[e].im = 0.0;
+            y[e].re = y[e].im = 0.0;
+        }
+        __syncwarp();
+        int it = 0;
+        for (it = 1; it <= n_iter; ++it) {
+            // ---- y' = TP(x + p) = t + ((I - Tr_out t) (x) I) / d
+            for (int e = lane; e < ss; e += 32) {
+                T[e].re = x[e].re + p[e].re;
+                T[e].im = x[e].im + p[e].im;
+            }
+            __syncwarp();
+            for (int e = lane; e < d * d; e += 32) {
+                const int i = e / d, j = e % d;
+                double re = 0.0, im = 0.0;
+                for (int a = 0; a < d; ++a) {
+                    const cplx z = T[(i * d + a) * s + (j * d + a)];
+                    re += z.re;
+                    im += z.im;
+                }
+                rin[e].re = ((i == j) ? 1.0 : 0.0) - re;
+                rin[e].im = -im;
+            }
+            __syncwarp();
+            double c1r = 0.0, c1i = 0.0;
+            for (int e = lane; e < ss; e += 32) {
+                const int r = e / s, c = e % s;
+                cplx yn = T[e];
+                if (r % d == c % d) {
+                    const cplx g = rin[(r / d) * d + (c / d)];
+                    yn.re += g.re * invd;
+                    yn.im += g.im * invd;
+                }
+                const double dr = yn.re - y[e].re, di = yn.im - y[e].im;
+                // conj(y_diff) * q
+                c1r += dr * q[e].re + di * q[e].im;
+                c1i += dr * q[e].im - di * q[e].re;
+                y[e] = yn;
+            }
+            c1r = warp_sum(c1r);
+            c1i = warp_sum(c1i);
+            __syncwarp();
+            // ---- x' = CP(y' + q): eigh, clip at 1e-12, recompose
+            for (int e = lane; e < ss; e += 32) {
+                const int r = e / s, c = e % s, et = c * s + r;
+                A[e].re = 0.5 * ((y[e].re + q[e].re) + (y[et].re + q[et].re));
+                A[e].im = 0.5 * ((y[e].im + q[e].im) - (y[et].im + q[et].im));
+            }
+            __syncwarp();
+            warp_jacobi<true>(A, V, rot, s, lane);
+            double c2r = 0.0, c2i = 0.0, c3 = 0.0;
+            for (int e = lane; e < ss; e += 32) {
+                const int r = e / s, c = e % s;
+                double re = 0.0, im = 0.0;
+                for (int j = 0; j < s; ++j) {
+                    const double lam = fmax(A[j * s + j].re, kClipChoi);
+                    const cplx u = V[r * s + j], v = V[c * s + j];
+                    re += lam * (u.re * v.re + u.im * v.im);
+                    im += lam * (u.im * v.re - u.re * v.im);
+                }
+                const double dr = re - x[e].re, di = im - x[e].im;
+                c2r += dr * p[e].re + di * p[e].im;
+                c2i += dr * p[e].im - di * p[e].re;
+                x[e].re = re;
+                x[e].im = im;
+                const double pr = re - y[e].re, pi = im - y[e].im;  // p_diff = x' - y'
+                p[e].re += pr;
+                p[e].im += pi;
+                q[e].re -= pr;
+                q[e].im -= pi;
+                c3 += pr * pr + pi * pi;
+            }
+            c2r = warp_sum(c2r);
+            c2i = warp_sum(c2i);
+            c3 = warp_sum(c3);
+            __syncwarp();
+            const double crit = 2.0 * (sqrt(c1r * c1r + c1i * c1i) + sqrt(c2r * c2r + c2i * c2i)) + 2.0 * c3;
+            if (crit < tol) break;
+        }
+        if (it > n_iter) it = n_iter;
+        cplx* dst = reinterpret_cast<cplx*>(choi_out) + b * ss;
+        for (int e = lane; e < ss; e += 32) dst[e] = x[e];
+        if (iters && lane == 0) iters[b] = it;
+        __syncwarp();
+    }
+}
+
+static int launch_cptp(int n, int B, const double* in, int n_iter, double tol, double* out, int32_t* iters,
+                       cudaStream_t st) {
+    const int d = 1 << n, s = d * d;
+    const int warps = (s >= 16) ? 4 : 8;
+    const size_t smem = warps * cptp_smem_per_warp(s);
+    QPB_REQUIRE(smem <= 227 * 1024, "CPTP projection needs %zu bytes of shared memory", smem);
+    if (smem > 48 * 1024) QPB_CUDA(cudaFuncSetAttribute(k_cptp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long blocks = ((long)B + warps - 1) / warps;
+    const long cap = (long)num_sms() * (s >= 16 ? 1 : 4);
+    if (blocks > cap) blocks = cap;
+    k_cptp<<<(int)blocks, warps * 32, smem, st>>>(d, B, in, n_iter, tol, out, iters);
+    QPB_LAUNCHED("k_cptp");
+    return QPB_OK;
+}
+
+}  // namespace qpb
+
+using namespace qpb;
+
+extern "C" {
+
+int qpb_process_plan_create(qpb_process_plan** out, int n_qubits, int S, int K, const double* Linv, void* stream) {
+    QPB_REQUIRE(out != nullptr, "plan output pointer is NULL");
+    QPB_REQUIRE(n_qubits >= 1 && n_qubits <= 2, "process tomography supports 1 or 2 qubits (got %d)", n_qubits);
+    QPB_REQUIRE(S >= 1 && K >= 1 && Linv != nullptr, "bad process plan arguments");
+    qpb_process_plan* p = new qpb_process_plan();
+    p->n = n_qubits;
+    p->d = 1 << n_qubits;
+    p->S = S;
+    p->K = K;
+    p->d4 = p->d * p->d * p->d * p->d;
+    const size_t bytes = sizeof(double) * 2 * (size_t)p->d4 * S * K;
+    int rc = check_cuda(cudaMalloc(&p->LinvT, bytes), "cudaMalloc LinvT");
+    if (rc != QPB_OK) {
+        delete p;
+        return rc;
+    }
+    const long total = (long)p->d4 * S * K;
+    const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    k_lifp_prep<<<grid, 256, 0, (cudaStream_t)stream>>>(Linv, p->d * p->d, S * K, p->LinvT);
+    QPB_LAUNCHED("k_lifp_prep");
+    *out = p;
+    return QPB_OK;
+}
+
+int qpb_process_plan_destroy(qpb_process_plan* p) {
+    if (!p) return QPB_OK;
+    cudaFree(p->LinvT);
+    delete p;
+    return QPB_OK;
+}
+
+int qpb_lifp_cptp(const qpb_process_plan* plan, int B, const int32_t* counts, int cptp, int n_iter, double tol,
+                  double* choi, int32_t* iters, void* stream) {
+    QPB_REQUIRE(plan != nullptr, "plan is NULL");
+    QPB_REQUIRE(B >= 0 && n_iter >= 0, "bad arguments");
+    if (B == 0) return QPB_OK;
+    QPB_REQUIRE(counts && choi, "NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cols = plan->S * plan->K;
+    const int warps = 8;
+    const size_t smem = sizeof(double) * (size_t)warps * cols;
+    QPB_REQUIRE(smem <= 200 * 1024, "S*K=%d too large", cols);
+    if (smem > 48 * 1024) QPB_CUDA(cudaFuncSetAttribute(k_lifp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long blocks = ((long)B + warps - 1) / warps;
+    const long cap = (long)num_sms() * 4;
+    if (blocks > cap) blocks = cap;
+    k_lifp<<<(int)blocks, warps * 32, smem, st>>>(plan->S, plan->K, plan->d4, B, plan->LinvT, counts, choi);
+    QPB_LAUNCHED("k_lifp");
+    if (cptp) return launch_cptp(plan->n, B, choi, n_iter, tol, choi, iters, st);
+    if (iters) QPB_CUDA(cudaMemsetAsync(iters, 0, sizeof(int32_t) * (size_t)B, st));
+    return QPB_OK;
+}
+
+int qpb_cptp_project(int n_qubits, int B, const double* choi_in, int n_iter, double tol, double* choi_out,
+                     int32_t* iters, void* stream) {
+    QPB_REQUIRE(n_qubits >= 1 && n_qubits <= 2, "CPTP projection supports 1 or 2 qubits (got %d)", n_qubits);
+    QPB_REQUIRE(B >= 0 && n_iter >= 0, "bad arguments");
+    if (B == 0) return QPB_OK;
+    QPB_REQUIRE(choi_in && choi_out, "NULL buffer");
+    return launch_cptp(n_qubits, B, choi_in, n_iter, tol, choi_out, iters, (cudaStream_t)stream);
+}
+
+}  // extern "C"

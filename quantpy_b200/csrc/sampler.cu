@@ -1,0 +1,192 @@
+// k2: Philox multinomial shot sampler, one warp per (resample, POVM).
+// Replaces np.random.multinomial(n_m, p_m) at quantpy/tomography/state.py:111-114.
+//
+// Every shot is an independent categorical draw through a Walker/Vose alias table held in shared
+// memory (one 32-bit uniform per shot: the high part of u*O picks the column, the low part is the
+// acceptance fraction).  Lanes histogram into lane-private shared-memory bins ([O][32] layout:
+// bank == lane, no conflicts and no atomics) when O <= 64, else into one per-warp histogram with
+// shared-memory atomics.  Counts therefore sum to n_shots exactly, and, like NumPy, the last
+// outcome's probability is the remainder 1 - sum(p[:-1]).
+//
+// RNG stream: Philox4x32-10, key = seed, counter = (draw block j, POVM m, global sample index):
+// results do not depend on the batch size or on how samples are sharded across GPUs.
+#include "../../include/quantpy_b200.h"
+#include "common.cuh"
+
+namespace qpb {
+
+constexpr int kMaxPovms = 256;
+constexpr int kPrivateBinsMaxO = 64;
+
+struct ShotVec {
+    int32_t n[kMaxPovms];
+};
+
+// Serial Vose construction by one thread.  q (O doubles) and stack (O ints) are scratch.
+__device__ void build_alias(const double* __restrict__ p, int O, double* q, int* stack, uint2* table) {
+    double head = 0.0;
+    for (int o = 0; o + 1 < O; ++o) {
+        double v = fmin(fmax(p[o], 0.0), 1.0);
+        q[o] = v;
+        head += v;
+    }
+    q[O - 1] = fmax(1.0 - head, 0.0);  // remainder, as NumPy's multinomial does
+    const double norm = (double)O / (head + q[O - 1]);
+    int ns = 0, nl = 0;  // small stack grows up from 0, large stack grows down from O-1
+    for (int o = 0; o < O; ++o) {
+        q[o] *= norm;
+        if (q[o] < 1.0) stack[ns++] = o;
+        else stack[O - 1 - nl++] = o;
+    }
+    while (ns > 0 && nl > 0) {
+        const int s = stack[--ns];
+        const int l = stack[O - nl];
+        --nl;
+        double t = q[s] * 4294967296.0;
+        table[s].x = (t >= 4294967295.0) ? 0xffffffffu : (uint32_t)t;
+        table[s].y = (uint32_t)l;
+        q[l] = (q[l] + q[s]) - 1.0;
+        if (q[l] < 1.0) stack[ns++] = l;
+        else stack[O - 1 - nl++] = l;
+    }
+    int fallback = 0;
+    for (int o = 1; o < O; ++o)
+        if (p[o] > p[fallback]) fallback = o;
+    while (nl > 0) {
+        const int l = stack[O - nl];
+        --nl;
+        table[l].x = 0xffffffffu;
+        table[l].y = (uint32_t)l;
+    }
+    while (ns > 0) {  // only reachable through rounding; never hand mass to a zero-probability outcome
+        const int s = stack[--ns];
+        const bool zero = !(q[s] > 0.5);
+        table[s].x = zero ? 0u : 0xffffffffu;
+        table[s].y = (uint32_t)(zero ? fallback : s);
+    }
+}
+
+__global__ void k_alias_build(const double* __restrict__ p, int rows, int O, double* q, int* stack, uint2* table) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    build_alias(p + (long)r * O, O, q + (long)r * O, stack + (long)r * O, table + (long)r * O);
+}
+
+__host__ __device__ inline size_t sampler_smem_per_warp(int O, int batched) {
+    size_t s = sizeof(uint2) * (size_t)O;
+    s += sizeof(uint32_t) * (size_t)O * (O <= kPrivateBinsMaxO ? 32 : 1);
+    if (batched) s += (sizeof(double) + sizeof(int)) * (size_t)O;
+    return (s + 15) & ~(size_t)15;
+}
+
+template <bool PRIVATE>
+__device__ __forceinline__ void tally(uint32_t u, int O, const uint2* __restrict__ table, uint32_t* hist, int lane) {
+    const uint64_t x = (uint64_t)u * (uint32_t)O;
+    const uint32_t col = (uint32_t)(x >> 32), frac = (uint32_t)x;
+    const uint2 e = table[col];
+    const uint32_t o = (frac < e.x) ? col : e.y;
+    if (PRIVATE) hist[o * 32 + lane] += 1;
+    else atomicAdd(&hist[o], 1u);
+}
+
+template <bool PRIVATE>
+__global__ void k_multinomial(int B, int P, int O, const double* __restrict__ p, int batched,
+                              const uint2* __restrict__ tables, ShotVec shots, uint32_t k0, uint32_t k1,
+                              uint64_t offset, int32_t* __restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    unsigned char* base = smraw + (size_t)warp * sampler_smem_per_warp(O, batched);
+    uint2* table = reinterpret_cast<uint2*>(base);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(table + O);
+    const int nbins = PRIVATE ? O * 32 : O;
+
+    const long items = (long)B * P;
+    for (long item = (long)blockIdx.x * nw + warp; item < items; item += (long)gridDim.x * nw) {
+        const long b = item / P;
+        const int m = (int)(item % P);
+        if (batched) {
+            double* q = reinterpret_cast<double*>(hist + nbins);
+            int* stack = reinterpret_cast<int*>(q + O);
+            if (lane == 0) build_alias(p + item * O, O, q, stack, table);
+        } else {
+            for (int o = lane; o < O; o += 32) table[o] = tables[(long)m * O + o];
+        }
+        for (int e = lane; e < nbins; e += 32) hist[e] = 0u;
+        __syncwarp();
+        const uint32_t n = (uint32_t)shots.n[m];
+        const uint32_t ncall = (n + 3u) >> 2;
+        const uint64_t sample = offset + (uint64_t)b;
+        for (uint32_t j = lane; j < ncall; j += 32) {
+            const philox4 r = philox4x32_10(j, (uint32_t)m, (uint32_t)sample, (uint32_t)(sample >> 32), k0, k1);
+            const uint32_t left = n - 4u * j;  // >= 1
+            tally<PRIVATE>(r.x, O, table, hist, lane);
+            if (left > 1) tally<PRIVATE>(r.y, O, table, hist, lane);
+            if (left > 2) tally<PRIVATE>(r.z, O, table, hist, lane);
+            if (left > 3) tally<PRIVATE>(r.w, O, table, hist, lane);
+        }
+        __syncwarp();
+        int32_t* out = counts + item * O;
+        for (int o = lane; o < O; o += 32) {
+            uint32_t s;
+            if (PRIVATE) {
+                s = 0;
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) s += hist[o * 32 + ((l + lane) & 31)];
+            } else {
+                s = hist[o];
+            }
+            out[o] = (int32_t)s;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace qpb
+
+using namespace qpb;
+
+extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batched, const int32_t* n_shots_host,
+                               uint64_t seed, uint64_t offset, int32_t* counts, void* stream) {
+    QPB_REQUIRE(B >= 0 && P >= 1 && O >= 1, "bad shape B=%d P=%d O=%d", B, P, O);
+    QPB_REQUIRE(P <= kMaxPovms, "P=%d exceeds the supported %d POVMs per tomograph", P, kMaxPovms);
+    if (B == 0) return QPB_OK;
+    QPB_REQUIRE(p && n_shots_host && counts, "NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    ShotVec shots;
+    for (int m = 0; m < P; ++m) {
+        QPB_REQUIRE(n_shots_host[m] >= 0, "negative shot count");
+        shots.n[m] = n_shots_host[m];
+    }
+    uint2* tables = nullptr;
+    double* q = nullptr;
+    int* stack = nullptr;
+    if (!p_batched) {
+        const size_t cells = (size_t)P * O;
+        QPB_CUDA(cudaMallocAsync(&tables, sizeof(uint2) * cells, st));
+        QPB_CUDA(cudaMallocAsync(&q, sizeof(double) * cells, st));
+        QPB_CUDA(cudaMallocAsync(&stack, sizeof(int) * cells, st));
+        k_alias_build<<<(P + 31) / 32, 32, 0, st>>>(p, P, O, q, stack, tables);
+        QPB_LAUNCHED("k_alias_build");
+    }
+    const bool priv = O <= kPrivateBinsMaxO;
+    int warps = 8;
+    size_t per = sampler_smem_per_warp(O, p_batched);
+    while (warps > 1 && warps * per > 96 * 1024) warps >>= 1;
+    const size_t smem = warps * per;
+    QPB_REQUIRE(smem <= 227 * 1024, "O=%d too large for the sampler", O);
+    auto kern = priv ? k_multinomial<true> : k_multinomial<false>;
+    if (smem > 48 * 1024) QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long items = (long)B * P;
+    long blocks = (items + warps - 1) / warps;
+    const long cap = (long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    kern<<<(int)blocks, warps * 32, smem, st>>>(B, P, O, p, p_batched, tables, shots, (uint32_t)seed,
+                                                (uint32_t)(seed >> 32), offset, counts);
+    QPB_LAUNCHED("k_multinomial");
+    if (!p_batched) {
+        QPB_CUDA(cudaFreeAsync(tables, st));
+        QPB_CUDA(cudaFreeAsync(q, st));
+        QPB_CUDA(cudaFreeAsync(stack, st));
+    }
+    return QPB_OK;
+}

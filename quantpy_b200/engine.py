@@ -1,0 +1,231 @@
+"""Device-side engine: thin Python wrappers that hand device pointers to libquantpy_b200.so.
+
+Everything here is plumbing -- tensors as device buffers, the current CUDA stream, plan caching.
+All arithmetic on the hot path happens inside the CUDA kernels (csrc/).  No function in this module
+has a CPU implementation; each raises NativeError when the library or a GPU is missing.
+"""
+
+import ctypes
+import hashlib
+
+import numpy as np
+
+from . import _native as nt
+from .routines import _left_inv
+
+
+def next_seed():
+    """Draw a 63-bit Philox key from NumPy's global legacy RNG, so that `np.random.seed(s)` makes
+    simulated experiments reproducible exactly where it does for the reference (state.py:112 uses the
+    same global stream; the stream itself is not reproduced)."""
+    return int(np.random.randint(0, 2**63 - 1, dtype=np.int64))
+
+
+def weighted_povm(povm_matrix, n_measurements):
+    """(K, D) shot-weighted POVM rows (quantpy/tomography/state.py:193-196)."""
+    povm_matrix = np.asarray(povm_matrix, dtype=np.float64)
+    n = np.asarray(n_measurements, dtype=np.float64).reshape(-1)
+    return np.reshape(povm_matrix * n[:, None, None] / n.sum(), (-1, povm_matrix.shape[-1]))
+
+
+def sample_counts(probs, n_samples, P, O, n_shots, seed, offset=0):
+    """qpb_multinomial: counts [B, P, O] int32 on the device.  probs: device [P*O] (shared by all
+    samples) or [B, P*O]; n_shots: host int array [P]."""
+    torch = nt.torch_cuda()
+    lib = nt.load_library()
+    batched = int(probs.dim() == 2 and probs.shape[0] == n_samples and n_samples > 1)
+    counts = torch.empty((n_samples, P, O), dtype=torch.int32, device="cuda")
+    shots = np.ascontiguousarray(np.asarray(n_shots, dtype=np.int32).reshape(-1))
+    if len(shots) != P:
+        raise ValueError("Wrong length for argument `n_measurements`")
+    nt.check(lib.qpb_multinomial(n_samples, P, O, nt.ptr(probs.contiguous()), batched,
+                                 shots.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(seed),
+                                 ctypes.c_uint64(offset), nt.ptr(counts), nt.stream_ptr()))
+    return counts
+
+
+class StatePlan:
+    """Device tables for one (POVM tensor, shot vector): wraps qpb_state_plan."""
+
+    def __init__(self, povm_matrix, n_measurements, need_lin=True):
+        torch = nt.torch_cuda()
+        lib = nt.load_library()
+        povm_matrix = np.asarray(povm_matrix, dtype=np.float64)
+        self.P, self.O, self.D = povm_matrix.shape
+        self.K = self.P * self.O
+        self.n_qubits = int(round(np.log2(self.D) / 2))
+        self.d = 2**self.n_qubits
+        if 4**self.n_qubits != self.D or not 1 <= self.n_qubits <= 4:
+            raise ValueError("POVM rows must have length 4^n with 1 <= n <= 4")
+        A = weighted_povm(povm_matrix, n_measurements)
+        self.A_dev = nt.to_device(A, torch.float64)
+        self.L_dev = nt.to_device(_left_inv(A), torch.float64) if need_lin else None
+        self.M_dev = nt.to_device(povm_matrix.reshape(self.K, self.D), torch.float64)
+        self.n_shots = np.asarray(np.rint(np.asarray(n_measurements, dtype=np.float64)), dtype=np.int32).reshape(-1)
+        handle = ctypes.c_void_p()
+        nt.check(lib.qpb_state_plan_create(ctypes.byref(handle), self.n_qubits, self.K, nt.ptr(self.A_dev),
+                                           nt.ptr(self.L_dev), nt.stream_ptr()))
+        self.handle = handle
+        self._lib = lib
+
+    def __del__(self):
+        handle = getattr(self, "handle", None)
+        if handle:
+            try:
+                self._lib.qpb_state_plan_destroy(handle)
+            except Exception:
+                pass
+            self.handle = None
+
+    # -- kernels ---------------------------------------------------------------------------------
+    def probabilities(self, bloch):
+        """clip(2^n M.r, 0, 1) for a batch of Bloch vectors -> device tensor [B, K] (k1)."""
+        torch = nt.torch_cuda()
+        r = nt.to_device(np.atleast_2d(np.asarray(bloch, dtype=np.float64)), torch.float64)
+        B = r.shape[0]
+        p = torch.empty((B, self.K), dtype=torch.float64, device="cuda")
+        nt.check(self._lib.qpb_povm_probs(self.K, self.D, B, nt.ptr(self.M_dev), nt.ptr(r), float(self.d), 1,
+                                          nt.ptr(p), nt.stream_ptr()))
+        return p
+
+    def sample(self, probs, n_samples, seed, offset=0):
+        """Multinomial counts [B, P, O] int32 on the device (k2).  probs: device [K] or [B, K]."""
+        return sample_counts(probs, n_samples, self.P, self.O, self.n_shots, seed, offset)
+
+    def lin(self, counts, physical=True):
+        """Linear inversion (+ projection) -> device float64 [B, d, d, 2] (k3-k5)."""
+        torch = nt.torch_cuda()
+        if self.L_dev is None:
+            raise nt.NativeError("plan was built without the linear-inversion table")
+        counts = counts.reshape(-1, self.K).contiguous()
+        B = counts.shape[0]
+        rho = torch.empty((B, self.d, self.d, 2), dtype=torch.float64, device="cuda")
+        nt.check(self._lib.qpb_lin_project(self.handle, B, nt.ptr(counts), int(bool(physical)), nt.ptr(rho),
+                                           nt.stream_ptr()))
+        return rho
+
+    def mle(self, counts, rho0=None, max_iter=100, tol=1e-3):
+        """R.rho.R maximum likelihood -> (rho [B, d, d, 2], iters [B] int32) on the device."""
+        torch = nt.torch_cuda()
+        counts = counts.reshape(-1, self.K).contiguous()
+        B = counts.shape[0]
+        rho = torch.empty((B, self.d, self.d, 2), dtype=torch.float64, device="cuda")
+        iters = torch.empty((B,), dtype=torch.int32, device="cuda")
+        nt.check(self._lib.qpb_mle_rrr(self.handle, B, nt.ptr(counts), nt.ptr(rho0), int(max_iter), float(tol),
+                                       nt.ptr(rho), nt.ptr(iters), nt.stream_ptr()))
+        return rho, iters
+
+    def estimate(self, counts, method="lin", physical=True, init="lin", max_iter=100, tol=1e-3):
+        """point_estimate dispatcher (state.py:143-189) on device counts -> (rho, iters or None)."""
+        if method == "lin":
+            return self.lin(counts, physical), None
+        if method == "mle":
+            if init == "lin":
+                start = self.lin(counts, True)  # state.py:209 -> point_estimate("lin"), physical by default
+            elif init == "mixed":
+                start = None
+            else:
+                raise ValueError("Invalid value for argument `init`")
+            return self.mle(counts, start, max_iter, tol)
+        raise ValueError("Invalid value for argument `method`")
+
+    def bootstrap(self, probs, n_samples, seed, offset, ref_matrix, method="lin", physical=True, init="lin",
+                  max_iter=100, tol=1e-3, dst="hs", keep=False):
+        """Fused bootstrap (interval.py:598-609) -> dict of device tensors: dist (+ rho, counts, iters)."""
+        torch = nt.torch_cuda()
+        if method not in nt.METHODS:
+            raise ValueError("Invalid value for argument `method`")
+        if init not in nt.INITS:
+            raise ValueError("Invalid value for argument `init`")
+        B = int(n_samples)
+        ref = nt.complex_to_device(ref_matrix)
+        dist = torch.empty((B,), dtype=torch.float64, device="cuda")
+        counts = torch.empty((B, self.P, self.O), dtype=torch.int32, device="cuda")
+        iters = torch.empty((B,), dtype=torch.int32, device="cuda")
+        rho = torch.empty((B, self.d, self.d, 2), dtype=torch.float64, device="cuda") if keep else None
+        nbytes = self._lib.qpb_bootstrap_state_workspace(self.handle, B, self.P, self.O)
+        work = torch.empty((max(int(nbytes), 8),), dtype=torch.uint8, device="cuda")
+        shots = np.ascontiguousarray(self.n_shots)
+        nt.check(self._lib.qpb_bootstrap_state(
+            self.handle, B, self.P, self.O, nt.ptr(probs.contiguous()), shots.ctypes.data_as(ctypes.c_void_p),
+            ctypes.c_uint64(seed), ctypes.c_uint64(offset), nt.METHODS[method], int(bool(physical)),
+            nt.INITS[init], int(max_iter), float(tol), nt.ptr(ref), nt.DIST_KINDS[dst], nt.ptr(dist),
+            nt.ptr(rho), nt.ptr(counts), nt.ptr(iters), nt.ptr(work), nt.stream_ptr()))
+        return {"dist": dist, "rho": rho, "counts": counts, "iters": iters, "_keepalive": (work, ref)}
+
+
+def distance(rho, ref_matrix, dst="hs"):
+    """dst(rho[b], ref) for a device batch rho [B, s, s, 2] -> device [B] (k8)."""
+    torch = nt.torch_cuda()
+    lib = nt.load_library()
+    B, s = rho.shape[0], rho.shape[1]
+    ref = nt.complex_to_device(ref_matrix)
+    out = torch.empty((B,), dtype=torch.float64, device="cuda")
+    nt.check(lib.qpb_distance(s, B, nt.ptr(rho.contiguous()), nt.ptr(ref), nt.DIST_KINDS[dst], nt.ptr(out),
+                              nt.stream_ptr()))
+    return out
+
+
+class ProcessPlan:
+    """Device tables for 'lifp' process estimation: wraps qpb_process_plan."""
+
+    def __init__(self, n_qubits, lifp_oper_inv, S, K):
+        nt.torch_cuda()
+        lib = nt.load_library()
+        self.n_qubits, self.S, self.K = n_qubits, S, K
+        self.s = 4**n_qubits
+        self.Linv_dev = nt.complex_to_device(np.asarray(lifp_oper_inv, dtype=np.complex128))
+        handle = ctypes.c_void_p()
+        nt.check(lib.qpb_process_plan_create(ctypes.byref(handle), n_qubits, S, K, nt.ptr(self.Linv_dev),
+                                             nt.stream_ptr()))
+        self.handle = handle
+        self._lib = lib
+
+    def __del__(self):
+        handle = getattr(self, "handle", None)
+        if handle:
+            try:
+                self._lib.qpb_process_plan_destroy(handle)
+            except Exception:
+                pass
+            self.handle = None
+
+    def lifp(self, counts, cptp=True, n_iter=1000, tol=1e-12):
+        """counts device int32 [B, S, K] -> (choi [B, s, s, 2], iters [B])."""
+        torch = nt.torch_cuda()
+        counts = counts.reshape(-1, self.S * self.K).contiguous()
+        B = counts.shape[0]
+        choi = torch.empty((B, self.s, self.s, 2), dtype=torch.float64, device="cuda")
+        iters = torch.empty((B,), dtype=torch.int32, device="cuda")
+        nt.check(self._lib.qpb_lifp_cptp(self.handle, B, nt.ptr(counts), int(bool(cptp)), int(n_iter), float(tol),
+                                         nt.ptr(choi), nt.ptr(iters), nt.stream_ptr()))
+        return choi, iters
+
+
+def cptp_project(choi_matrices, n_qubits, n_iter=1000, tol=1e-12):
+    """Alternating TP/CP projection (process.py:231-257) of host Choi matrices [B, s, s] on the GPU."""
+    torch = nt.torch_cuda()
+    lib = nt.load_library()
+    x = nt.complex_to_device(np.asarray(choi_matrices, dtype=np.complex128))
+    B = x.shape[0]
+    out = torch.empty_like(x)
+    iters = torch.empty((B,), dtype=torch.int32, device="cuda")
+    nt.check(lib.qpb_cptp_project(n_qubits, B, nt.ptr(x), int(n_iter), float(tol), nt.ptr(out), nt.ptr(iters),
+                                  nt.stream_ptr()))
+    return out, iters
+
+
+_PLAN_CACHE = {}
+
+
+def state_plan(povm_matrix, n_measurements):
+    """Plans are cached by content so that repeated point_estimate calls reuse the uploaded tables."""
+    povm_matrix = np.ascontiguousarray(np.asarray(povm_matrix, dtype=np.float64))
+    n = np.ascontiguousarray(np.asarray(n_measurements, dtype=np.float64).reshape(-1))
+    key = (povm_matrix.shape, hashlib.blake2b(povm_matrix.tobytes() + n.tobytes(), digest_size=16).digest())
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        if len(_PLAN_CACHE) >= 16:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        plan = _PLAN_CACHE[key] = StatePlan(povm_matrix, n)
+    return plan

@@ -1,0 +1,180 @@
+"""Bootstrap confidence intervals -- drop-in for the bootstrap functors of
+quantpy/tomography/interval.py (ConfidenceInterval :19-56, BootstrapStateInterval :542-612,
+BootstrapProcessInterval :615-685).
+
+The reference runs `n_points` serial Python iterations of experiment -> point_estimate -> dst.  Here
+the whole loop is one batched pass on the GPU (engine.StatePlan.bootstrap / ProcessPlan.lifp), sharded
+over the ranks of torch.distributed when a process group exists, followed by one all-gather of the
+per-sample distances, a sort and the same interp1d quantile function.
+"""
+
+from abc import ABC, abstractmethod
+from enum import Enum, auto
+
+import numpy as np
+
+from .. import _native as nt
+from .. import engine, parallel
+from .state import dst_kind
+
+
+class Mode(Enum):
+    STATE = auto()
+    CHANNEL = auto()
+
+
+def _pop_hidden_keys(kwargs):
+    """Constructor kwargs become attributes, minus self/tmg/dunder names (interval.py:858-865)."""
+    return {k: v for k, v in kwargs.items() if k not in ("self", "tmg") and not k.startswith("__")}
+
+
+class ConfidenceInterval(ABC):
+    """Functor: interval(conf_levels) -> (distances, conf_levels); `setup` runs lazily on first call."""
+
+    EPS = 1e-15
+
+    def __init__(self, tmg, **kwargs):
+        self.tmg = tmg
+        if hasattr(tmg, "state"):
+            self.mode = Mode.STATE
+        elif hasattr(tmg, "channel"):
+            self.mode = Mode.CHANNEL
+        else:
+            raise ValueError()
+        for name, value in kwargs.items():
+            setattr(self, name, value)
+
+    def __call__(self, conf_levels=None):
+        if conf_levels is None:
+            conf_levels = np.linspace(1e-3, 1 - 1e-3, 1000)
+        if not hasattr(self, "cl_to_dist"):
+            self.setup()
+        return self.cl_to_dist(conf_levels), conf_levels
+
+    @abstractmethod
+    def setup(self):
+        """Configure the confidence interval."""
+
+    def _finish(self, local_dist, n_points):
+        """All-gather the per-rank distances, keep them (sorted) and build the quantile function."""
+        full = parallel.all_gather_concat(local_dist, n_points)
+        self.dist = np.sort(full.cpu().numpy())
+        self.cl_to_dist = parallel.quantile_function(self.dist)
+
+
+class BootstrapStateInterval(ConfidenceInterval):
+    def __init__(self, tmg, n_points=1000, method="lin", physical=True, init="lin", tol=1e-3, max_iter=100,
+                 state=None):
+        """Parametric bootstrap around `state` (default: the tomograph's reconstructed state) with the
+        tomograph's POVM and shot numbers; kwargs as StateTomograph.point_estimate."""
+        super().__init__(tmg, **_pop_hidden_keys(locals()))
+
+    def setup(self, seed=None):
+        if self.mode == Mode.CHANNEL:
+            raise NotImplementedError("This interval works only for state tomography")
+        if self.state is None:
+            if hasattr(self.tmg, "reconstructed_state"):
+                self.state = self.tmg.reconstructed_state
+            else:
+                self.state = self.tmg.point_estimate(method=self.method, physical=self.physical, init=self.init,
+                                                     tol=self.tol, max_iter=self.max_iter)
+        if self.method == "mle-constr":
+            raise NotImplementedError("'mle-constr' (SLSQP) is outside the B200 hot path; use 'mle'")
+        if self.method not in ("lin", "mle"):
+            raise ValueError("Invalid value for argument `method`")
+        rank, size = parallel.world()
+        lo, hi = parallel.shard_bounds(self.n_points, rank, size)
+        seed = parallel.broadcast_seed(engine.next_seed() if seed is None else int(seed))
+        plan = engine.state_plan(self.tmg.povm_matrix, self.tmg.n_measurements)
+        probs = plan.probabilities(self.state.bloch)[0]
+        kind = dst_kind(self.tmg.dst)
+        out = plan.bootstrap(probs, hi - lo, seed, lo, self.state.matrix, self.method, self.physical, self.init,
+                             self.max_iter, self.tol, kind or "hs", keep=kind is None)
+        if kind is None:  # user-supplied measure: evaluate it on the reconstructed batch
+            from ..qobj import Qobj
+
+            torch = nt.torch_cuda()
+            rhos = nt.complex_to_host(out["rho"])
+            local = torch.tensor([float(self.tmg.dst(Qobj(r), self.state)) for r in rhos], dtype=torch.float64,
+                                 device="cuda")
+        else:
+            local = out["dist"]
+        self.iters = out["iters"].cpu().numpy()
+        self._finish(local, self.n_points)
+
+
+class BootstrapProcessInterval(ConfidenceInterval):
+    def __init__(self, tmg, n_points=1000, method="lifp", cptp=True, tol=1e-10, channel=None,
+                 states_est_method="lin", states_physical=True, states_init="lin"):
+        """Parametric bootstrap around `channel` (default: the tomograph's reconstructed channel);
+        kwargs as ProcessTomograph.point_estimate."""
+        super().__init__(tmg, **_pop_hidden_keys(locals()))
+
+    def setup(self, seed=None):
+        if self.mode == Mode.STATE:
+            raise NotImplementedError("This interval works only for process tomography")
+        if self.channel is None:
+            if hasattr(self.tmg, "reconstructed_channel"):
+                self.channel = self.tmg.reconstructed_channel
+            else:
+                self.channel = self.tmg.point_estimate(method=self.method, states_physical=self.states_physical,
+                                                       states_init=self.states_init, cptp=self.cptp)
+        if self.method not in ("lifp", "states"):
+            raise ValueError("Incorrect value for argument `method`")
+        rank, size = parallel.world()
+        lo, hi = parallel.shard_bounds(self.n_points, rank, size)
+        seed = parallel.broadcast_seed(engine.next_seed() if seed is None else int(seed))
+        first = self.tmg.tomographs[0]
+        boot = self.tmg.__class__(self.channel, self.tmg.input_states, self.tmg.dst)
+        centre = self.channel.choi.matrix
+        kind = dst_kind(self.tmg.dst)
+        torch = nt.torch_cuda()
+        if self.method == "lifp":
+            counts = boot.sample_counts(hi - lo, first.n_measurements, first.povm_matrix, seed, lo, device=True)
+            boot.experiment(first.n_measurements, first.povm_matrix)  # gives boot its POVM / shot bookkeeping
+            choi = boot.point_estimate_batch(counts, cptp=self.cptp, device=True)
+            if kind is not None:
+                local = engine.distance(choi, centre, kind)
+            else:
+                from ..qobj import Qobj
+
+                local = torch.tensor([float(self.tmg.dst(Qobj(c), self.channel.choi))
+                                      for c in nt.complex_to_host(choi)], dtype=torch.float64, device="cuda")
+        else:
+            counts = boot.sample_counts(hi - lo, first.n_measurements, first.povm_matrix, seed, lo)
+            boot.experiment(first.n_measurements, first.povm_matrix)
+            vals = []
+            for table in counts:
+                boot.results = table
+                est = boot.point_estimate(method="states", states_est_method=self.states_est_method,
+                                          states_physical=self.states_physical, states_init=self.states_init,
+                                          cptp=self.cptp)
+                vals.append(float(self.tmg.dst(est.choi, self.channel.choi)))
+            local = torch.tensor(vals, dtype=torch.float64, device="cuda")
+        self._finish(local, self.n_points)
+
+
+def _out_of_scope(name):
+    class _Unavailable(ConfidenceInterval):
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(
+                f"{name} is outside the B200 bootstrap hot path (analytic / LP / MCMC interval, see DESIGN.md); "
+                "use the reference implementation for it."
+            )
+
+        def setup(self):  # pragma: no cover
+            raise NotImplementedError
+
+    _Unavailable.__name__ = _Unavailable.__qualname__ = name
+    return _Unavailable
+
+
+MomentInterval = _out_of_scope("MomentInterval")
+MomentFidelityStateInterval = _out_of_scope("MomentFidelityStateInterval")
+MomentFidelityProcessInterval = _out_of_scope("MomentFidelityProcessInterval")
+SugiyamaInterval = _out_of_scope("SugiyamaInterval")
+PolytopeStateInterval = _out_of_scope("PolytopeStateInterval")
+PolytopeProcessInterval = _out_of_scope("PolytopeProcessInterval")
+HolderInterval = _out_of_scope("HolderInterval")
+MHMCStateInterval = _out_of_scope("MHMCStateInterval")
+MHMCProcessInterval = _out_of_scope("MHMCProcessInterval")

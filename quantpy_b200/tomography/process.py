@@ -1,0 +1,169 @@
+"""ProcessTomograph -- drop-in for quantpy/tomography/process.py on the B200 path.
+
+  experiment        one state tomography per input state          (process.py:91-129) -> sampler kernel
+  point_estimate    'lifp' linear inversion of the Choi matrix    (process.py:194-213, 284-289) -> qpb_lifp_cptp
+                    'states' assembly from reconstructed outputs  (process.py:316-327) -> state kernels + host basis algebra
+  cptp_projection   alternating TP / CP projection                (process.py:231-278) -> qpb_cptp_project
+
+The 'lifp' operator and its left inverse are built once per (POVM, shots) and kept on the device;
+the reference rebuilds both on every call.  'pgdb' is broken in the reference and is
+not provided.
+"""
+
+import numpy as np
+
+from .. import _native as nt
+from .. import engine
+from ..basis import Basis
+from ..channel import Channel
+from ..measurements import generate_measurement_matrix
+from ..qobj import Qobj
+from ..routines import _left_inv, _out_ptrace_oper, generate_pauli, generate_single_entries, kron
+from .state import StateTomograph, resolve_dst
+
+
+def _generate_input_states(input_states, n_qubits):
+    """Named sets are the Bloch rows of the POVM of that name, normalised to unit trace (process.py:330-339)."""
+    if isinstance(input_states, list):
+        return input_states
+    rows = np.squeeze(generate_measurement_matrix(input_states, n_qubits))
+    states = []
+    for bloch in rows:
+        state = Qobj(bloch)
+        states.append(state / state.trace())
+    return states
+
+
+class ProcessTomograph:
+    def __init__(self, channel, input_states="proj4", dst="hs"):
+        self.channel = channel
+        self.dst = resolve_dst(dst)
+        self.input_states = input_states
+        self.input_basis = Basis(_generate_input_states(input_states, channel.n_qubits))
+        if self.input_basis.dim != 4**channel.n_qubits:
+            raise ValueError("Input states do not constitute a basis")
+        self._decomposed_single_entries = np.array(
+            [self.input_basis.decompose(Qobj(unit)) for unit in generate_single_entries(2**channel.n_qubits)]
+        )
+        self._ptrace_oper = _out_ptrace_oper(channel.n_qubits)
+        self._ptrace_dag_ptrace = self._ptrace_oper.T.conj() @ self._ptrace_oper
+        self._plan_key = None
+        self._plan = None
+
+    # -- experiment ------------------------------------------------------------------------------
+    def _output_states(self):
+        return [self.channel.transform(state) for state in self.input_basis.elements]
+
+    def experiment(self, n_measurements, povm="proj-set", warm_start=False):
+        """Simulate process tomography: a state tomography of every transformed input state."""
+        if not warm_start:
+            self.tomographs = [StateTomograph(out) for out in self._output_states()]
+        for tmg in self.tomographs:
+            tmg.experiment(n_measurements, povm, warm_start=warm_start)
+
+    def sample_counts(self, n_samples, n_measurements, povm="proj-set", seed=None, offset=0, device=False):
+        """`n_samples` simulated process tomographies at once -> counts [n_samples, S, P, O].
+
+        All S output states are sampled by one kernel launch: the (state, POVM) pairs are presented to
+        the sampler as S*P independent multinomials."""
+        n = self.channel.n_qubits
+        povm_matrix = generate_measurement_matrix(povm, n)
+        P, O = povm_matrix.shape[:2]
+        shots = np.ones(P) * n_measurements if np.issubdtype(type(n_measurements), np.integer) else np.asarray(
+            n_measurements)
+        if len(shots) != P:
+            raise ValueError("Wrong length for argument `n_measurements`")
+        outs = self._output_states()
+        S = len(outs)
+        plan = engine.state_plan(povm_matrix, shots)
+        probs = plan.probabilities(np.array([o.bloch for o in outs]))  # [S, K]
+        shots_all = np.tile(np.rint(np.asarray(shots, dtype=np.float64)).astype(np.int32), S)
+        counts = engine.sample_counts(probs.reshape(-1), int(n_samples), S * P, O, shots_all,
+                                      engine.next_seed() if seed is None else int(seed), int(offset))
+        counts = counts.reshape(int(n_samples), S, P, O)
+        return counts if device else counts.cpu().numpy().astype(np.int64)
+
+    @property
+    def results(self):
+        assert hasattr(self, "tomographs"), "No results"
+        return np.asarray([stmg.results for stmg in self.tomographs])
+
+    @results.setter
+    def results(self, results):
+        assert hasattr(self, "tomographs"), "Call experiment first"
+        for stmg, stmg_results in zip(self.tomographs, results):
+            stmg.results = stmg_results
+
+    # -- reconstruction --------------------------------------------------------------------------
+    def _weighted_povm(self):
+        first = self.tomographs[0]
+        return engine.weighted_povm(first.povm_matrix, first.n_measurements)
+
+    def _process_plan(self):
+        """Build (once per POVM/shots) the lifp operator of process.py:197-209 and upload its left inverse."""
+        A = self._weighted_povm()
+        key = A.tobytes()
+        if self._plan_key != key:
+            n = self.channel.n_qubits
+            d = 2**n
+            E = np.tensordot(A, generate_pauli(n), axes=1)  # (K, d, d) POVM operators
+            rho_t = np.array([state.matrix.T for state in self.input_basis.elements])
+            # row(s, k) = vec(rho_s (x) E_k^T) = (rho_s^T (x) E_k) flattened row-major
+            self._lifp_oper = np.einsum("sij,kab->skiajb", rho_t, E).reshape(len(rho_t) * len(E), d**4)
+            self._lifp_oper_inv = _left_inv(self._lifp_oper)
+            self._plan = engine.ProcessPlan(n, self._lifp_oper_inv, len(rho_t), len(E))
+            self._plan_key = key
+        return self._plan
+
+    def point_estimate_batch(self, counts, cptp=True, n_iter=1000, tol=1e-12, return_iters=False, device=False):
+        """'lifp' estimates for a batch of count tables [B, S, P, O] -> Choi matrices [B, d^2, d^2]."""
+        torch = nt.torch_cuda()
+        plan = self._process_plan()
+        if not torch.is_tensor(counts):
+            counts = nt.to_device(np.asarray(counts).reshape(-1, plan.S * plan.K), torch.int32)
+        choi, iters = plan.lifp(counts, cptp, n_iter, tol)
+        if device:
+            return (choi, iters) if return_iters else choi
+        out = nt.complex_to_host(choi)
+        return (out, iters.cpu().numpy()) if return_iters else out
+
+    def point_estimate(self, method="lifp", cptp=True, n_iter=1000, tol=1e-10, states_est_method="lin",
+                       states_physical=True, states_init="lin"):
+        """Reconstruct the channel from `results` (process.py:142-229).
+
+        method : 'lifp' (linear inversion) | 'states' (assemble from reconstructed output states)
+        cptp : project the estimate onto completely positive trace-preserving maps
+        """
+        self._process_plan()
+        self._unnorm_results = np.hstack([stmg.flat_results for stmg in self.tomographs])
+        if method == "lifp":
+            return self._point_estimate_lifp(cptp=cptp)
+        if method == "states":
+            return self._point_estimate_states(cptp, states_est_method, states_physical, states_init, n_iter, tol)
+        if method == "pgdb":
+            raise NotImplementedError("'pgdb' is broken in the reference and not part of the B200 path")
+        raise ValueError("Incorrect value for argument `method`")
+
+    def cptp_projection(self, channel, n_iter=1000, tol=1e-12):
+        """Alternating TP/CP projection of a channel (process.py:231-257), on the GPU."""
+        choi, _ = engine.cptp_project(channel.choi.matrix[None], self.channel.n_qubits, n_iter, tol)
+        return Channel(nt.complex_to_host(choi)[0])
+
+    def _point_estimate_lifp(self, cptp):
+        self.frequencies = np.hstack([s.flat_results / s.flat_results.sum() for s in self.tomographs])
+        choi = self.point_estimate_batch(self.results[None], cptp=cptp)[0]  # lifp ignores n_iter/tol like process.py:287
+        self.reconstructed_channel = Channel(choi)
+        return self.reconstructed_channel
+
+    def _point_estimate_states(self, cptp, method, physical, init, n_iter, tol):
+        # the reference forwards (n_iter, tol) positionally into StateTomograph.point_estimate (process.py:317)
+        outputs = [tmg.point_estimate(method, physical, init, n_iter, tol) for tmg in self.tomographs]
+        output_basis = Basis(outputs)
+        dim = output_basis.dim
+        choi = Qobj(np.zeros((dim, dim), dtype=np.complex128))
+        for coefs in self._decomposed_single_entries:
+            choi += kron(self.input_basis.compose(coefs), output_basis.compose(coefs))
+        self.reconstructed_channel = Channel(choi)
+        if cptp and not self.reconstructed_channel.is_cptp(verbose=False):
+            self.reconstructed_channel = self.cptp_projection(self.reconstructed_channel)
+        return self.reconstructed_channel

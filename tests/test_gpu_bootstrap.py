@@ -1,0 +1,211 @@
+"""GPU tests of the fused bootstrap (state) and of the process path."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import bootstrap as oboot  # noqa: E402
+from oracle import distances as odist  # noqa: E402
+from oracle import process as oproc  # noqa: E402
+from oracle import state as ostate  # noqa: E402
+
+
+def fro(a, b):
+    return np.sqrt(np.sum(np.abs(np.asarray(a) - np.asarray(b)) ** 2, axis=(-2, -1)))
+
+
+def haar(n, seed, rank=None):
+    rng = np.random.default_rng(seed)
+    d = 2**n
+    k = d if rank is None else rank
+    g = rng.normal(size=(d, k)) + 1j * rng.normal(size=(d, k))
+    rho = g @ g.conj().T
+    return rho / np.trace(rho)
+
+
+@pytest.fixture(scope="module")
+def qp():
+    import quantpy_b200
+
+    return quantpy_b200
+
+
+@pytest.mark.parametrize("n,povm,method,dst", [(1, "proj-set", "lin", "hs"), (1, "proj-set", "mle", "trace"),
+                                               (2, "proj", "mle", "hs"), (2, "proj", "lin", "if"),
+                                               (3, "proj", "lin", "hs")])
+def test_fused_bootstrap_is_consistent_with_oracle(qp, n, povm, method, dst):
+    """Every stage of the fused call is re-derived by the oracle from the counts the GPU sampled:
+    reconstruction and distance agree to 1e-10 sample by sample."""
+    from quantpy_b200 import engine
+
+    rho = haar(n, 60 + n)
+    tmg = qp.StateTomograph(qp.Qobj(rho), dst=dst)
+    np.random.seed(n)
+    tmg.experiment(10000, povm)
+    plan = engine.state_plan(tmg.povm_matrix, tmg.n_measurements)
+    probs = plan.probabilities(tmg.state.bloch)[0]
+    B = 400 if n < 3 else 120
+    out = plan.bootstrap(probs, B, 11, 0, rho, method=method, max_iter=50, tol=1e-4, dst=dst, keep=True)
+    counts = out["counts"].cpu().numpy()
+    from quantpy_b200 import _native as nt
+
+    got = nt.complex_to_host(out["rho"])
+    if method == "lin":
+        want = ostate.lin_estimate(counts, tmg.povm_matrix, tmg.n_measurements)
+    else:
+        want, wits = ostate.mle_rrr(counts, tmg.povm_matrix, tmg.n_measurements, max_iter=50, tol=1e-4,
+                                    return_iters=True)
+        assert np.array_equal(out["iters"].cpu().numpy(), wits)
+    assert fro(got, want).max() < 1e-10
+    assert np.abs(out["dist"].cpu().numpy() - odist.BY_NAME[dst](want, rho)).max() < 1e-10
+
+
+@pytest.mark.parametrize("method", ["lin", "mle"])
+def test_bootstrap_interval_matches_reference_distribution(qp, golden, method):
+    """BootstrapStateInterval against the oracle's serial loop (different RNG streams): the quantile
+    functions agree within Monte-Carlo error (two-sample KS test)."""
+    from scipy import stats
+
+    g = golden("boot_c2_lin")
+    tmg = qp.StateTomograph(qp.Qobj(g["rho_true"]))
+    tmg.povm_matrix = g["povm_matrix"]
+    tmg.results = g["counts"]
+    tmg.n_measurements = g["n_meas"]
+    tmg.reconstructed_state = qp.Qobj(g["centre"])
+    itv = qp.BootstrapStateInterval(tmg, n_points=4000, method=method, tol=1e-6, max_iter=200)
+    np.random.seed(3)
+    dist, cl = itv()
+    assert dist.shape == (1000,) and np.all(np.diff(dist) >= 0)
+    assert itv.cl_to_dist.x[0] == 0 and itv.cl_to_dist.x[-1] == 1 and len(itv.cl_to_dist.y) == 4000
+    np.random.seed(4)
+    ref = oboot.bootstrap_state(g["centre"], g["povm_matrix"], g["n_meas"], 300, method=method, mle="rrr",
+                                tol=1e-6, max_iter=200)
+    assert stats.ks_2samp(itv.dist, ref).pvalue > 1e-3
+    with pytest.raises(ValueError):
+        itv.cl_to_dist(1.5)
+    # reproducible under np.random.seed, like the reference
+    a = qp.BootstrapStateInterval(tmg, n_points=64, method=method)
+    b = qp.BootstrapStateInterval(tmg, n_points=64, method=method)
+    np.random.seed(8)
+    a.setup()
+    np.random.seed(8)
+    b.setup()
+    assert np.array_equal(a.dist, b.dist)
+
+
+def test_bootstrap_full_size_properties(qp):
+    """BASELINE config 2 at full size (1e5 resamples): size-independent properties."""
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    rho = haar(2, 5)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(0)
+    tmg.experiment(10000, "proj")
+    plan = engine.state_plan(tmg.povm_matrix, tmg.n_measurements)
+    probs = plan.probabilities(tmg.state.bloch)[0]
+    B = 100000
+    out = plan.bootstrap(probs, B, 1, 0, rho, method="mle", max_iter=200, tol=1e-6, keep=True)
+    counts = out["counts"].cpu().numpy()
+    assert np.array_equal(counts.sum((1, 2)), np.full(B, 10000))
+    est = nt.complex_to_host(out["rho"])
+    assert np.abs(np.trace(est, axis1=1, axis2=2) - 1).max() < 1e-12
+    assert np.abs(est - est.conj().transpose(0, 2, 1)).max() == 0
+    assert np.linalg.eigvalsh(est).min() > -1e-13
+    iters = out["iters"].cpu().numpy()
+    assert iters.min() >= 1 and iters.max() <= 200
+    # the MLE never has a worse likelihood than its linear-inversion start (spot check)
+    idx = np.arange(0, B, 997)
+    start = ostate.lin_estimate(counts[idx], tmg.povm_matrix, tmg.n_measurements)
+    for i, j in enumerate(idx):
+        assert ostate.neg_log_likelihood(est[j], counts[j], tmg.povm_matrix, tmg.n_measurements) <= \
+            ostate.neg_log_likelihood(start[i], counts[j], tmg.povm_matrix, tmg.n_measurements) + 1e-12
+    # a prefix of the batch reproduces exactly (global-index keyed RNG, deterministic kernels)
+    again = plan.bootstrap(probs, 1000, 1, 0, rho, method="mle", max_iter=200, tol=1e-6)
+    assert np.array_equal(again["dist"].cpu().numpy(), out["dist"].cpu().numpy()[:1000])
+    d = out["dist"].cpu().numpy()
+    assert np.abs(d[idx] - odist.hs(est[idx], rho)).max() < 1e-12
+
+
+def test_bootstrap_custom_distance_and_errors(qp):
+    rho = haar(1, 9)
+    tmg = qp.StateTomograph(qp.Qobj(rho), dst=lambda a, b: float(np.abs(a.matrix - b.matrix).max()))
+    np.random.seed(0)
+    tmg.experiment(1000, "proj-set")
+    itv = qp.BootstrapStateInterval(tmg, n_points=50)
+    itv.setup()
+    assert itv.dist.shape == (50,) and itv.dist.max() < 0.2
+    ch = qp.ProcessTomograph(qp.channel.depolarizing(0.1, 1), "sic")
+    with pytest.raises(NotImplementedError):
+        qp.BootstrapStateInterval(ch).setup()
+    with pytest.raises(NotImplementedError):
+        qp.BootstrapProcessInterval(tmg).setup()
+
+
+# ----------------------------------------------------------------------------- process path
+
+def process_tomograph(qp, g, n):
+    chan = qp.channel.depolarizing(0.1, n)
+    tmg = qp.ProcessTomograph(chan, "sic")
+    np.random.seed(0)
+    tmg.experiment(10000, "proj-set")
+    return tmg
+
+
+def test_process_input_json(qp, golden):
+    """The reference's only shipped known-input run (input.json + scripts/process_interval.py --no-ci)."""
+    g = golden("process")
+    inputs = [qp.Qobj(m) for m in g["json_inputs"]]
+    tmg = qp.ProcessTomograph(qp.channel.depolarizing(n_qubits=1), input_states=inputs)
+    np.random.seed(0)
+    tmg.experiment(1000, "proj-set")
+    tmg.results = g["json_outcomes"]
+    est = tmg.point_estimate(cptp=False)
+    assert fro(est.choi.matrix, g["json_choi"]) < 1e-10
+    assert np.abs(est.choi.bloch - g["json_choi_bloch"]).max() < 1e-10
+    assert fro(tmg.point_estimate(cptp=True).choi.matrix, g["json_choi_cptp"]) < 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 2])
+def test_process_lifp_and_cptp_match_reference(qp, golden, n):
+    g = golden("process")
+    tmg = process_tomograph(qp, g, n)
+    counts = g[f"dep{n}_counts"]
+    assert tmg.results.shape == counts.shape[1:]
+    raw = tmg.point_estimate_batch(counts, cptp=False)
+    assert fro(raw, g[f"dep{n}_lifp_raw"]).max() < 1e-10
+    proj, iters = tmg.point_estimate_batch(counts, cptp=True, return_iters=True)
+    want, wit = oproc.cptp_projection(g[f"dep{n}_lifp_raw"], return_iters=True)
+    assert fro(proj, g[f"dep{n}_lifp_cptp"]).max() < 1e-9
+    assert fro(proj, want).max() < 1e-9 and np.abs(iters - wit).max() <= 1
+    tmg.results = counts[0]
+    st = tmg.point_estimate("states", cptp=True)
+    assert fro(st.choi.matrix, g[f"dep{n}_states_cptp"][0]) < 1e-9
+    one = tmg.cptp_projection(qp.Channel(g[f"dep{n}_lifp_raw"][0]))
+    assert fro(one.choi.matrix, want[0]) < 1e-9
+    with pytest.raises(ValueError):
+        tmg.point_estimate("nope")
+
+
+def test_process_bootstrap(qp, golden):
+    from scipy import stats
+
+    g = golden("process")
+    tmg = process_tomograph(qp, g, 1)
+    tmg.results = g["boot1_counts"]
+    tmg.reconstructed_channel = qp.Channel(g["boot1_centre"])
+    itv = qp.BootstrapProcessInterval(tmg, n_points=2000)
+    np.random.seed(1)
+    dist, cl = itv([0.1, 0.5, 0.9])
+    assert np.all(np.diff(dist) > 0)
+    inputs = oproc.input_states("sic", 1)
+    np.random.seed(2)
+    ref = oboot.bootstrap_process(g["boot1_centre"], inputs, g["dep1_povm"], g["dep1_n_meas"], 200)
+    assert stats.ks_2samp(itv.dist, ref).pvalue > 1e-3
+    # counts sampled for the bootstrap are consistent with the channel outputs
+    counts = tmg.sample_counts(300, 10000, "proj-set", seed=3)
+    assert counts.shape == (300, 4, 3, 2) and (counts.sum(-1) == 10000).all()
+    probs = np.array([ostate.probabilities(g["dep1_povm"], __import__("oracle").pauli.matrix_to_bloch(o))
+                      for o in g["dep1_outputs"]])
+    assert np.abs(counts.mean(0) / 10000 - probs).max() < 5e-3

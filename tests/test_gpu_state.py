@@ -1,0 +1,268 @@
+"""GPU parity tests of the state path: CUDA kernels (through the C ABI / Python shim) against the CPU
+oracle and against reference outputs stored in tests/golden.  Tolerances are written in each test:
+bit-exact for integer stages, 1e-10 Frobenius for FP64 stages on identical counts."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import distances as odist  # noqa: E402
+from oracle import pauli as opauli  # noqa: E402
+from oracle import state as ostate  # noqa: E402
+
+STATE_CASES = ["state_c1", "state_c1_pure", "state_c2", "state_c2_set", "state_c2_rank1", "state_c2_sic",
+               "state_c3", "state_c3_rank2", "state_c4"]
+
+
+def fro(a, b):
+    return np.sqrt(np.sum(np.abs(np.asarray(a) - np.asarray(b)) ** 2, axis=(-2, -1)))
+
+
+def haar(n, seed, rank=None):
+    rng = np.random.default_rng(seed)
+    d = 2**n
+    k = d if rank is None else rank
+    g = rng.normal(size=(d, k)) + 1j * rng.normal(size=(d, k))
+    rho = g @ g.conj().T
+    return rho / np.trace(rho)
+
+
+@pytest.fixture(scope="module")
+def qp():
+    import quantpy_b200
+
+    return quantpy_b200
+
+
+def tomograph(qp, g):
+    tmg = qp.StateTomograph(qp.Qobj(g["rho_true"]))
+    tmg.povm_matrix = g["povm_matrix"]
+    tmg.results = g["counts"][0]
+    tmg.n_measurements = g["n_meas"]
+    return tmg
+
+
+# ----------------------------------------------------------------------------- probabilities, sampler
+
+@pytest.mark.parametrize("case", STATE_CASES)
+def test_probabilities_match_reference(qp, golden, case):
+    from quantpy_b200 import engine
+
+    g = golden(case)
+    plan = engine.state_plan(g["povm_matrix"], g["n_meas"])
+    p = plan.probabilities(opauli.matrix_to_bloch(g["rho_true"])).cpu().numpy().reshape(g["probs"].shape)
+    assert np.abs(p - g["probs"]).max() < 1e-14
+
+
+@pytest.mark.parametrize("n,povm", [(1, "proj-set"), (2, "proj"), (2, "proj-set"), (3, "proj"), (4, "proj")])
+def test_sampler_counts_sum_and_chi_square(qp, n, povm):
+    """Integer stage: every POVM's counts sum to the shot number exactly.  Distribution: chi-square per
+    outcome against the exact probabilities (NumPy's stream is not reproduced)."""
+    from scipy import stats
+
+    rho = haar(n, 10 + n)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    shots = 10000
+    B = 2000 if n < 4 else 200
+    counts = tmg.sample_counts(B, shots, povm, seed=123)
+    povm_matrix = qp.generate_measurement_matrix(povm, n)
+    assert counts.shape == (B,) + povm_matrix.shape[:2]
+    assert counts.dtype == np.int64
+    assert np.array_equal(counts.sum(-1), np.full(counts.shape[:2], shots))
+    probs = ostate.probabilities(povm_matrix, opauli.matrix_to_bloch(rho))
+    # pooled chi-square per POVM (B*shots draws), then the per-sample statistic's mean
+    for m in range(povm_matrix.shape[0]):
+        pooled = counts[:, m].sum(0)
+        expect = probs[m] / probs[m].sum() * pooled.sum()
+        keep = expect > 20
+        stat = ((pooled[keep] - expect[keep]) ** 2 / expect[keep]).sum()
+        dof = keep.sum() - 1
+        assert stats.chi2.sf(stat, dof) > 1e-4, (m, stat, dof)
+    # variance check on one outcome: binomial variance n p (1-p)
+    k = int(np.argmax(probs[0]))
+    pk = probs[0, k] / probs[0].sum()
+    var = counts[:, 0, k].var()
+    assert abs(var / (shots * pk * (1 - pk)) - 1) < (0.15 if n < 4 else 0.4)
+
+
+def test_sampler_is_shard_invariant_and_seeded(qp):
+    """The draw for a global sample index does not depend on the batch split (multi-GPU sharding)."""
+    tmg = qp.StateTomograph(qp.Qobj(haar(2, 3)))
+    full = tmg.sample_counts(64, 10000, "proj", seed=99)
+    a = tmg.sample_counts(40, 10000, "proj", seed=99, offset=0)
+    b = tmg.sample_counts(24, 10000, "proj", seed=99, offset=40)
+    assert np.array_equal(full, np.concatenate([a, b]))
+    other = tmg.sample_counts(64, 10000, "proj", seed=100)
+    assert not np.array_equal(full, other)
+    np.random.seed(5)
+    x = tmg.sample_counts(4, 10000, "proj")
+    np.random.seed(5)
+    y = tmg.sample_counts(4, 10000, "proj")
+    assert np.array_equal(x, y)
+
+
+def test_sampler_edge_cases(qp):
+    # a pure |0> state: z- outcome has probability exactly 0 and must never appear
+    tmg = qp.StateTomograph(qp.Qobj([1, 0], is_ket=True))
+    counts = tmg.sample_counts(500, [7, 1, 12345], "proj-set", seed=1)
+    assert np.array_equal(counts.sum(-1), np.tile([7, 1, 12345], (500, 1)))
+    assert counts[:, 2, 1].max() == 0 and (counts[:, 2, 0] == 12345).all()
+    assert tmg.sample_counts(0, 10, "proj-set", seed=1).shape == (0, 3, 2)
+    with pytest.raises(ValueError):
+        tmg.sample_counts(3, [1, 2], "proj-set")
+
+
+# ----------------------------------------------------------------------------- linear inversion
+
+@pytest.mark.parametrize("case", STATE_CASES)
+def test_lin_matches_reference_outputs(qp, golden, case):
+    """Reference counts in -> rho within 1e-10 (Frobenius) of the reference's own output."""
+    g = golden(case)
+    tmg = tomograph(qp, g)
+    for physical, key in ((True, "lin_physical"), (False, "lin_raw")):
+        got = tmg.point_estimate_batch(g["counts"], "lin", physical=physical)
+        assert fro(got, g[key]).max() < 1e-10
+    one = tmg.point_estimate("lin")
+    assert fro(one.matrix, g["lin_physical"][0]) < 1e-10
+    assert fro(tmg.reconstructed_state.matrix, one.matrix) == 0
+
+
+@pytest.mark.parametrize("n,B", [(1, 3000), (2, 3000), (3, 600), (4, 40)])
+def test_lin_matches_oracle_on_gpu_counts(qp, n, B):
+    rho = haar(n, 20 + n, rank=None if n != 3 else 2)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(n)
+    tmg.experiment(10000, "proj")
+    counts = tmg.sample_counts(B, 10000, "proj", seed=n)
+    got = tmg.point_estimate_batch(counts, "lin")
+    want = ostate.lin_estimate(counts, tmg.povm_matrix, tmg.n_measurements)
+    assert fro(got, want).max() < 1e-10
+    assert np.abs(np.trace(got, axis1=1, axis2=2) - 1).max() < 1e-12
+    assert np.linalg.eigvalsh(got).min() > 0
+
+
+# ----------------------------------------------------------------------------- maximum likelihood
+
+@pytest.mark.parametrize("case", ["state_c1", "state_c1_pure", "state_c2", "state_c2_set", "state_c2_rank1",
+                                  "state_c2_sic", "state_c3", "state_c3_rank2"])
+@pytest.mark.parametrize("init", ["lin", "mixed"])
+def test_mle_fixed_iterations_match_oracle(qp, golden, case, init):
+    """Same update, same start, same number of iterations -> 1e-10."""
+    g = golden(case)
+    tmg = tomograph(qp, g)
+    iters = 40 if g["rho_true"].shape[0] <= 4 else 12
+    got, its = tmg.point_estimate_batch(g["counts"], "mle", init=init, max_iter=iters, tol=0.0, return_iters=True)
+    want = ostate.mle_rrr(g["counts"], g["povm_matrix"], g["n_meas"], init=init, max_iter=iters, tol=0.0)
+    assert (its == iters).all()
+    assert fro(got, want).max() < 1e-10
+
+
+def test_mle_four_qubits_matches_oracle(qp, golden):
+    g = golden("state_c4")
+    tmg = tomograph(qp, g)
+    got = tmg.point_estimate_batch(g["counts"], "mle", max_iter=3, tol=0.0)
+    want = ostate.mle_rrr(g["counts"], g["povm_matrix"], g["n_meas"], max_iter=3, tol=0.0)
+    assert fro(got, want).max() < 1e-10
+
+
+@pytest.mark.parametrize("n,povm,B", [(1, "proj-set", 2000), (2, "proj", 2000), (2, "proj-set", 500)])
+@pytest.mark.parametrize("tol,max_iter", [(1e-3, 100), (1e-6, 300)])
+def test_mle_tolerance_mode_matches_oracle(qp, n, povm, B, tol, max_iter):
+    """Per-sample stopping: iteration counts equal the oracle's and states agree to 1e-10."""
+    rho = haar(n, 40 + n)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(n)
+    tmg.experiment(10000, povm)
+    counts = tmg.sample_counts(B, 10000, povm, seed=5)
+    got, its = tmg.point_estimate_batch(counts, "mle", max_iter=max_iter, tol=tol, return_iters=True)
+    want, wits = ostate.mle_rrr(counts, tmg.povm_matrix, tmg.n_measurements, max_iter=max_iter, tol=tol,
+                                return_iters=True)
+    same = its == wits
+    assert same.mean() > 0.999  # a step norm within rounding of tol may stop one iteration apart
+    assert fro(got[same], want[same]).max() < 1e-10
+    assert 1 < its.mean() < max_iter
+
+
+@pytest.mark.parametrize("case", ["state_c1", "state_c2", "state_c2_set", "state_c2_rank1", "state_c2_sic"])
+def test_mle_is_at_least_as_likely_as_reference(qp, golden, case):
+    """Loose pin to the reference's BFGS 'mle' (SURVEY D1): our likelihood is never worse."""
+    g = golden(case)
+    tmg = tomograph(qp, g)
+    got = tmg.point_estimate_batch(g["counts"], "mle", max_iter=20000, tol=1e-13)
+    for i, c in enumerate(g["counts"]):
+        ours = ostate.neg_log_likelihood(got[i], c, g["povm_matrix"], g["n_meas"])
+        ref = ostate.neg_log_likelihood(g["mle_default"][i], c, g["povm_matrix"], g["n_meas"])
+        assert ours <= ref + 1e-9
+
+
+def test_mle_edge_cases(qp):
+    tmg = qp.StateTomograph(qp.Qobj([1, 0], is_ket=True))
+    np.random.seed(0)
+    tmg.experiment(10000, "proj-set")  # contains an outcome with zero counts
+    assert tmg.results[2, 1] == 0
+    counts = np.repeat(tmg.results[None], 5, axis=0)
+    got, its = tmg.point_estimate_batch(counts, "mle", max_iter=500, tol=1e-9, return_iters=True)
+    want, wits = ostate.mle_rrr(counts, tmg.povm_matrix, tmg.n_measurements, max_iter=500, tol=1e-9,
+                                return_iters=True)
+    assert np.isfinite(got).all() and np.array_equal(its, wits)
+    assert fro(got, want).max() < 1e-10
+    # max_iter = 0 returns the start state; empty batch is allowed
+    start = tmg.point_estimate_batch(counts, "lin")
+    assert fro(tmg.point_estimate_batch(counts, "mle", max_iter=0), start).max() < 1e-15
+    assert tmg.point_estimate_batch(counts[:0], "mle").shape == (0, 2, 2)
+    with pytest.raises(ValueError):
+        tmg.point_estimate("nope")
+    with pytest.raises(ValueError):
+        tmg.point_estimate("mle", init="nope")
+    with pytest.raises(NotImplementedError):
+        tmg.point_estimate("mle-constr")
+
+
+# ----------------------------------------------------------------------------- distances
+
+@pytest.mark.parametrize("case", STATE_CASES)
+def test_distances_match_reference(qp, golden, case):
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    g = golden(case)
+    est = nt.complex_to_device(g["lin_physical"])
+    hs = engine.distance(est, g["rho_true"], "hs").cpu().numpy()
+    tr = engine.distance(est, g["rho_true"], "trace").cpu().numpy()
+    inf = engine.distance(est, g["rho_true"], "if").cpu().numpy()
+    assert np.abs(hs - g["dist_hs"]).max() < 1e-13
+    assert np.abs(tr - g["dist_trace"]).max() < 1e-10
+    tol = 1e-7 if case.endswith(("pure", "rank1", "rank2")) else 1e-10  # scipy sqrtm near singular
+    assert np.abs(inf - g["dist_if"]).max() < tol
+    assert np.abs(inf - odist.infidelity(g["lin_physical"], g["rho_true"])).max() < 1e-10
+    same = engine.distance(est[:1], g["lin_physical"][0], "hs").cpu().numpy()
+    assert same[0] == 0.0
+
+
+# ----------------------------------------------------------------------------- single-experiment API
+
+def test_state_tomograph_api(qp):
+    rho = haar(2, 77)
+    tmg = qp.StateTomograph(qp.Qobj(rho), dst="trace")
+    assert tmg.dst is qp.trace_dst
+    np.random.seed(1)
+    tmg.experiment(1000)  # default 'proj-set'
+    assert tmg.povm_matrix.shape == (9, 4, 16)
+    assert tmg.results.shape == (9, 4) and tmg.results.dtype == np.int64
+    assert np.array_equal(tmg.n_measurements, np.full(9, 1000.0))
+    assert tmg.flat_results.shape == (36,)
+    first = tmg.results.copy()
+    tmg.experiment(500, warm_start=True)
+    assert tmg.results.shape == (18, 4) and np.array_equal(tmg.results[:9], first)
+    assert np.array_equal(tmg.n_measurements, np.r_[np.full(9, 1000), np.full(9, 500)])
+    est = tmg.point_estimate("lin")
+    want = ostate.lin_estimate(tmg.results, tmg.povm_matrix, tmg.n_measurements)
+    assert fro(est.matrix, want) < 1e-10
+    # results setter recomputes n_measurements exactly (integer stage)
+    tmg.results = first
+    assert np.array_equal(tmg.n_measurements, first.sum(-1)) and tmg.n_measurements.dtype == np.int64
+    with pytest.raises(ValueError):
+        tmg.experiment([10, 20], "proj-set")
+    with pytest.raises(ValueError):
+        qp.StateTomograph(qp.Qobj(rho), dst="nope")

@@ -1,0 +1,214 @@
+"""CPU tests: host-side mirror of the reference API, the C-ABI library's exports, and the
+multi-rank plumbing (gloo, world_size 2).  No kernel is launched here."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import quantpy_b200 as qp
+from quantpy_b200 import _native, parallel
+from quantpy_b200.routines import _left_inv, _mat2vec, _out_ptrace_oper, _vec2mat
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_qobj_representations(golden):
+    g = golden("api")
+    for n in (1, 2, 3):
+        q = qp.Qobj(g[f"rho_{n}"])
+        assert q.n_qubits == n
+        assert np.allclose(q.bloch, g[f"bloch_{n}"], atol=1e-15)
+        assert np.allclose(qp.Qobj(g[f"bloch_{n}"]).matrix, g[f"back_{n}"], atol=1e-15)
+    assert np.allclose(qp.Qobj([0, 1], is_ket=True).bloch, g["ket01_bloch"])
+    assert np.allclose(qp.Qobj([0.5, 0, 0, 0.5]).matrix, [[1, 0], [0, 0]])
+    short = qp.Qobj([0.1, 0.2, 0.3])  # 4^n - 1 entries: identity coefficient is prepended
+    assert np.allclose(short.bloch, [0.5, 0.1, 0.2, 0.3])
+    rho2 = qp.Qobj(g["rho_2"])
+    assert np.allclose(rho2.ptrace([0]).matrix, g["ptrace_keep0"])
+    assert np.allclose(rho2.ptrace([1]).matrix, g["ptrace_keep1"])
+    assert rho2.is_density_matrix() and not rho2.is_pure()
+    assert qp.Qobj([1, 0], is_ket=True).is_pure()
+    with pytest.raises(ValueError):
+        qp.Qobj(np.zeros((2, 2, 2)))
+
+
+def test_qobj_arithmetic():
+    a = qp.Qobj(np.array([[1, 0], [0, 0]], dtype=complex))
+    b = qp.Qobj(np.array([[0, 0], [0, 1]], dtype=complex))
+    assert np.allclose((a + b).matrix, np.eye(2))
+    assert np.allclose((0.5 * a + b * 0.5).matrix, np.eye(2) / 2)
+    assert np.allclose((np.complex128(2) * a).matrix, 2 * a.matrix)
+    assert np.allclose((a / a.trace()).matrix, a.matrix)
+    assert np.allclose(a.kron(b).matrix, np.kron(a.matrix, b.matrix))
+    assert np.allclose(qp.kron(a, b).matrix, np.kron(a.matrix, b.matrix))
+    c = a.copy()
+    c += b
+    assert np.allclose(c.matrix, np.eye(2)) and np.allclose(a.matrix, [[1, 0], [0, 0]])
+    assert a == qp.Qobj(a) and a != b
+    with pytest.raises(ValueError):
+        a * "x"
+
+
+def test_measurement_matrices(golden):
+    g = golden("api")
+    for name in ("proj", "proj-set", "proj4", "sic"):
+        for n in (1, 2):
+            assert np.array_equal(qp.generate_measurement_matrix(name, n), g[f"povm_{name}_{n}"])
+    one = qp.generate_measurement_matrix("proj", 1)[0]
+    assert np.array_equal(qp.generate_measurement_matrix(one, 2), g["povm_proj_2"])
+    full = g["povm_proj-set_2"]
+    assert qp.generate_measurement_matrix(full, 2) is full
+    assert qp.generate_measurement_matrix(full[0], 2).shape == (1, 4, 16)
+    for bad in ("nope", np.zeros((3, 5)), 3):
+        with pytest.raises(ValueError):
+            qp.generate_measurement_matrix(bad, 2)
+
+
+def test_channel_and_basis(golden):
+    g = golden("api")
+    chan = qp.channel.depolarizing(p=0.3, n_qubits=1)
+    assert np.allclose(chan.choi.matrix, g["dep03_choi"], atol=1e-15)
+    by_choi = qp.Channel(g["dep03_choi"])
+    assert np.allclose(by_choi.transform(qp.Qobj(g["rho_1"])).matrix, g["dep03_apply"], atol=1e-15)
+    assert np.allclose(qp.operator.Z.as_channel().choi.matrix, g["zchan_choi"])
+    assert chan.is_cptp() and not qp.Channel(-g["dep03_choi"]).is_cptp(verbose=False)
+    kraus = qp.Channel(chan.kraus)
+    assert np.allclose(kraus.choi.matrix, g["dep03_choi"], atol=1e-12)
+    sic = [qp.Qobj(b) for b in np.squeeze(qp.generate_measurement_matrix("sic", 1))]
+    basis = qp.basis.Basis(sic)
+    assert np.allclose(basis.gram, g["basis_gram"], atol=1e-15)
+    coefs = basis.decompose(qp.Qobj(g["rho_1"]))
+    assert np.allclose(coefs, g["basis_decomp"], atol=1e-13)
+    with pytest.raises(ValueError):
+        qp.Channel(lambda r: r)
+    with pytest.raises(ValueError):
+        qp.ProcessTomograph(chan, input_states=sic[:3])
+
+
+def test_distances_host(golden):
+    g = golden("api")
+    a, b = g["dst_a"], g["dst_b"]
+    got = [qp.hs_dst(a, b), qp.trace_dst(qp.Qobj(a), qp.Qobj(b)), qp.if_dst(a, b)]
+    assert np.allclose(got, g["dst_vals"], atol=1e-13)
+    assert qp.hs_dst(a, a) == 0 and isinstance(qp.hs_dst(a, a), int)
+    assert np.isclose(qp.product(a, b), np.trace(a @ b.conj().T))
+
+
+def test_routines_match_oracle():
+    from oracle import process as oproc
+
+    rng = np.random.default_rng(0)
+    m = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    assert np.array_equal(_mat2vec(m), oproc.mat2vec(m)) and np.array_equal(_vec2mat(_mat2vec(m)), m)
+    for n in (1, 2):
+        assert np.array_equal(_out_ptrace_oper(n), oproc.ptrace_operator(n))
+    a = rng.normal(size=(6, 4)) + 1j * rng.normal(size=(6, 4))
+    assert np.allclose(_left_inv(a) @ a, np.eye(4))
+    assert np.allclose(qp.generate_pauli(2)[7], np.kron(qp.generate_pauli(1)[1], qp.generate_pauli(1)[3]))
+
+
+def test_out_of_scope_intervals_say_so():
+    class Fake:
+        state = None
+
+    for cls in (qp.MomentInterval, qp.SugiyamaInterval, qp.MHMCStateInterval, qp.HolderInterval):
+        with pytest.raises(NotImplementedError):
+            cls(Fake())
+
+
+def test_no_cpu_fallback():
+    """Without a GPU the product path must fail loudly, never compute on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    tmg = qp.StateTomograph(qp.Qobj([0.5, 0, 0, 0.5]))
+    with pytest.raises(qp.NativeError):
+        tmg.experiment(100)
+    tmg.povm_matrix = qp.generate_measurement_matrix("proj-set", 1)
+    tmg.results = np.array([[50, 50], [50, 50], [100, 0]])
+    with pytest.raises(qp.NativeError):
+        tmg.point_estimate("lin")
+    with pytest.raises(qp.NativeError):
+        qp.BootstrapStateInterval(tmg, n_points=4, state=tmg.state).setup()
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "quantpy_b200")):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, name)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), name
+                assert "/root/reference" not in text, name
+
+
+# ----------------------------------------------------------------------------- C ABI
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "quantpy_b200.h")).read()
+    declared = set(re.findall(r"QPB_API\s+[\w\s\*]+?\b(qpb_\w+)\s*\(", header))
+    assert len(declared) >= 17
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    lib = _native.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.qpb_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (qpb_\w+)", out))
+    assert exported == declared
+    assert lib.qpb_launch_count() == 0
+    # argument validation happens before any CUDA call: usable without a GPU
+    assert lib.qpb_distance(3, 1, None, None, 0, None, None) < 0
+    assert b"unsupported" in lib.qpb_last_error()
+    handle = ctypes.c_void_p()
+    assert lib.qpb_state_plan_create(ctypes.byref(handle), 7, 4, None, None, None) < 0
+
+
+# ----------------------------------------------------------------------------- multi-rank plumbing
+
+def test_shard_bounds_partition():
+    for n, w in ((100000, 8), (10, 3), (5, 8), (0, 2)):
+        cuts = [parallel.shard_bounds(n, r, w) for r in range(w)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        sizes = [hi - lo for lo, hi in cuts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from quantpy_b200 import parallel
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, size = parallel.world()
+n = 11
+lo, hi = parallel.shard_bounds(n, rank, size)
+seed = parallel.broadcast_seed(1234 + rank)
+assert seed == 1234
+# each rank "computes" the statistic of its slice of global sample indices
+local = torch.arange(lo, hi, dtype=torch.float64) * 0.5 + seed
+full = parallel.all_gather_concat(local, n)
+assert torch.equal(full, torch.arange(n, dtype=torch.float64) * 0.5 + 1234), full
+q = parallel.quantile_function(full.numpy()[::-1])
+assert np.isclose(q(0.0), 1234.0) and np.isclose(q(1.0), 1239.0) and np.isclose(q(0.5), 1236.5)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_all_gather_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o
