@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Benchmark of the tomography-bootstrap hot path (BASELINE.json metric:
+"MLE bootstrap reconstructions/sec (n-qubit Pauli POVM)").
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+One *step* = one pass of the hot path over one batch per GPU: sample B count tables from the centre
+state's POVM probabilities (Philox multinomial), reconstruct each (physical linear inversion ->
+R.rho.R maximum likelihood) and take its Hilbert-Schmidt distance to the centre -- i.e. the body of
+quantpy/tomography/interval.py:598-609 for B = n_points resamples.  The workload is BASELINE.json
+configs[1] (2 qubits, 36-outcome Pauli 'proj' POVM, 1e4 shots, 1e5 resamples); under torchrun every
+rank processes its own 1e5 resamples of the global index range (weak scaling, no data-path
+collective; the e2e leg adds the one all-gather of distances).
+
+`value`    reconstructions/s with inputs resident in HBM, CUDA-event timed per step, L2 flushed
+           between steps, max over ranks.
+`e2e`      the same metric through the public API (BootstrapStateInterval.setup) with host inputs
+           and host outputs inside the timed region.
+`roofline` for the dominant kernel (k_mle_rrr_small): algorithmic FP64 flops / CUDA-event duration of
+           that kernel alone, against the FP64 FMA peak measured live by qpb_fp64_fma_probe
+           (MEASURED_PEAKS.json has no FP64 figure); HBM GB/s is reported beside it.
+`cpu_baseline`  the oracle's port of the reference algorithm (SciPy BFGS 'mle') timed on one host core.
+
+--impl reference times that CPU port on all host cores and prints the same JSON shape.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MLE bootstrap reconstructions/sec (2-qubit Pauli POVM)"
+UNIT = "reconstructions/s"
+
+
+def haar_mixed(n, seed):
+    rng = np.random.default_rng(seed)
+    d = 2**n
+    g = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    rho = g @ g.conj().T
+    return rho / np.trace(rho)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-qubits", type=int, default=2)
+    ap.add_argument("--povm", default="proj")
+    ap.add_argument("--shots", type=int, default=10000)
+    ap.add_argument("--resamples", type=int, default=100000, help="bootstrap resamples per GPU per step")
+    ap.add_argument("--method", default="mle", choices=["mle", "lin"])
+    ap.add_argument("--tol", type=float, default=1e-6, help="MLE step-norm stopping threshold")
+    ap.add_argument("--max-iter", type=int, default=1000, help="MLE iteration cap")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--state-seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"BASELINE configs[1]: {args.n_qubits}-qubit Haar-random state (seed {args.state_seed}), "
+                    f"{6**args.n_qubits if args.povm == 'proj' else '?'}-outcome Pauli '{args.povm}' POVM, "
+                    f"{args.shots} shots, {args.resamples} {args.method.upper()} bootstrap resamples per GPU per step",
+        "n_qubits": args.n_qubits, "povm": args.povm, "shots": args.shots,
+        "resamples_per_gpu": args.resamples, "global_resamples": args.resamples * world,
+        "method": args.method, "mle_update": "R.rho.R", "init": "lin", "tol": args.tol, "max_iter": args.max_iter,
+        "dst": "hs", "l2": "flushed between timed steps (512 MiB write)", "sharding": f"resamples x{world}",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(names, r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (oracle port of the reference algorithm)
+# ------------------------------------------------------------------------------------------------
+def _cpu_chunk(seed, n_points, centre, povm, n_meas, method, tol, max_iter, mle):
+    import warnings
+
+    from threadpoolctl import threadpool_limits
+
+    from oracle import bootstrap as oboot
+
+    warnings.filterwarnings("ignore")
+    rng = np.random.RandomState(seed)
+    with threadpool_limits(1):  # one BLAS thread per worker: the matrices are 4x4, threads only contend
+        t0 = time.perf_counter()
+        oboot.bootstrap_state(centre, povm, n_meas, n_points, method=method, tol=tol, max_iter=max_iter, mle=mle,
+                              rng=rng, sort=False)
+        return time.perf_counter() - t0
+
+
+def cpu_baseline(args, centre, povm, n_meas):
+    """Reference algorithm (oracle port: experiment -> lin -> SciPy BFGS 'mle' -> hs_dst) on ONE core, on a
+    bounded sample of the same workload; plus the NumPy R.rho.R port for an apples-to-apples figure."""
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    done, spent, chunk = 0, 0.0, 8
+    while spent < args.cpu_seconds * 0.7:
+        spent += _cpu_chunk(1000 + done, chunk, centre, povm, n_meas, args.method, args.tol, args.max_iter, "bfgs")
+        done += chunk
+    out = {"value": done / spent, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"{done} resamples of the same workload through oracle.bootstrap.bootstrap_state "
+                     f"(reference algorithm: lin start + SciPy BFGS mle, tol={args.tol}, max_iter={args.max_iter}), "
+                     f"{spent:.1f} s on 1 core (the reference is single-threaded); host has {os.cpu_count()} cores"}
+    if args.method == "mle":
+        from oracle import state as ostate
+        from oracle.pauli import matrix_to_bloch
+
+        rng = np.random.RandomState(5)
+        nb = 2000
+        counts = ostate.experiment(povm, matrix_to_bloch(centre), n_meas, size=nb, rng=rng)
+        t0 = time.perf_counter()
+        ostate.mle_rrr(counts, povm, n_meas, max_iter=args.max_iter, tol=args.tol)
+        dt = time.perf_counter() - t0
+        out["rrr_numpy_port"] = {"value": nb / dt, "unit": UNIT, "cores": 1,
+                                 "sample": f"{nb} resamples, vectorised NumPy R.rho.R oracle (same update and stopping "
+                                           f"rule as the CUDA kernel), {dt:.1f} s"}
+    return out
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle port) on all host cores; rank 0 only."""
+    if rank != 0:
+        return
+    import warnings
+    from concurrent.futures import ProcessPoolExecutor
+
+    from oracle import state as ostate
+
+    warnings.filterwarnings("ignore")
+    centre = haar_mixed(args.n_qubits, args.state_seed)
+    povm = ostate.measurement_matrix(args.povm, args.n_qubits)
+    n_meas = np.ones(povm.shape[0]) * args.shots
+    cores = os.cpu_count() or 1
+    # size one step to ~3 s of wall time from a short probe
+    probe = _cpu_chunk(1, 4, centre, povm, n_meas, args.method, args.tol, args.max_iter, "bfgs") / 4
+    per_core = max(2, min(400, int(3.0 / max(probe, 1e-4))))
+    cfg = workload_config(args, world)
+    times = []
+    with ProcessPoolExecutor(max_workers=cores) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            futs = [pool.submit(_cpu_chunk, 100 * step + c, per_core, centre, povm, n_meas, args.method, args.tol,
+                                args.max_iter, "bfgs") for c in range(cores)]
+            [f.result() for f in futs]
+            if step >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    total = float(np.sum(times))
+    value = per_core * cores * args.steps / total
+    # the same loop with the reference's own default stopping parameters (tol=1e-3, max_iter=100), 1 core
+    t_def = _cpu_chunk(7, 40, centre, povm, n_meas, args.method, 1e-3, 100, "bfgs")
+    sample = (f"each step = {per_core * cores} resamples ({per_core} per core x {cores} processes) of the same workload "
+              f"through the oracle port of the reference algorithm (lin start + SciPy BFGS mle)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": cfg, "gpu_launches": 0,
+            "api_defaults_1core": {"value": 40 / t_def, "unit": UNIT, "tol": 1e-3, "max_iter": 100,
+                                   "note": "reference algorithm with StateTomograph.point_estimate's default tol/max_iter"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import quantpy_b200 as qp
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = nt.load_library()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, B = args.n_qubits, args.resamples
+    centre = haar_mixed(n, args.state_seed)
+    state = qp.Qobj(centre)
+    povm = qp.generate_measurement_matrix(args.povm, n)
+    n_meas = np.ones(povm.shape[0]) * args.shots
+    plan = engine.state_plan(povm, n_meas)
+    probs = plan.probabilities(state.bloch)[0].contiguous()       # resident inputs
+    ref = nt.complex_to_device(centre)
+    bufs = plan.bootstrap_buffers(B)
+    flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    kw = dict(method=args.method, physical=True, init="lin", max_iter=args.max_iter, tol=args.tol, dst="hs")
+    seed = 1234
+
+    def step(i):
+        # Philox counter = global sample index: rank r owns [r*B, (r+1)*B) of step i's range
+        plan.bootstrap_into(bufs, probs, ref, seed + i, rank * B, **kw)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    lib.qpb_reset_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i, (e0, e1) in enumerate(evs):
+        flush.zero_()                      # evict the previous step's data from the 126 MB L2 (not timed)
+        e0.record()
+        step(args.warmup + i)
+        e1.record()
+    barrier()
+    launches = int(lib.qpb_launch_count())
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_s = max_over_ranks(float(np.sum(step_ms)) / 1e3)
+    mean_iters = float(bufs["iters"].double().mean().item())
+    value = world * B * args.steps / total_s
+
+    # ---- e2e: the public API, host inputs -> host outputs, every step ------------------------------
+    tmg = qp.StateTomograph(state)
+    tmg.povm_matrix, tmg.n_measurements = povm, n_meas
+    tmg.results = np.zeros(povm.shape[:2], dtype=np.int64)  # bookkeeping only; the centre is given explicitly
+    tmg.n_measurements = n_meas
+    e2e_steps = max(2, min(args.steps, 5))
+    h2d = probs.numel() * 8 + state.bloch.size * 8 + ref.numel() * 8
+    d2h = (B * 8 + B * 4)
+    e2e_times = []
+    for i in range(1 + e2e_steps):
+        barrier()
+        t0 = time.perf_counter()
+        itv = qp.BootstrapStateInterval(tmg, n_points=B * world, method=args.method, tol=args.tol,
+                                        max_iter=args.max_iter, state=state)
+        itv.setup(seed=seed + 100 + i)
+        _ = itv.cl_to_dist(0.95)
+        barrier()
+        if i > 0:
+            e2e_times.append(time.perf_counter() - t0)
+    e2e_s = max_over_ranks(float(np.sum(e2e_times)))
+    e2e_value = world * B * e2e_steps / e2e_s
+    clock_info = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel, timed alone ------------------------------------------------
+    roof = hbm = None
+    if args.method == "mle":
+        counts = bufs["counts"]
+        start = plan.lin(counts, True)
+        rho = torch.empty_like(start)
+        iters = torch.empty((B,), dtype=torch.int32, device="cuda")
+        reps = 5
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        torch.cuda.synchronize()
+        for e0, e1 in kev:
+            flush.zero_()
+            e0.record()
+            nt.check(lib.qpb_mle_rrr(plan.handle, B, nt.ptr(counts), nt.ptr(start), args.max_iter, args.tol,
+                                     nt.ptr(rho), nt.ptr(iters), nt.stream_ptr()))
+            e1.record()
+        torch.cuda.synchronize()
+        k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
+        K, D, d = plan.K, plan.D, plan.d
+        tot_iters = float(iters.double().sum().item())
+        flops = tot_iters * (4 * K * D + 16 * d**3) + 2.0 * K * D * B
+        # FP64 peak, measured now on this device
+        sink = torch.zeros(8, dtype=torch.float64, device="cuda")
+        probe_flops = np.zeros(1)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 0.0
+        for _ in range(3):
+            p0.record()
+            import ctypes
+            nt.check(lib.qpb_fp64_fma_probe(200000, nt.ptr(sink), probe_flops.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                            nt.stream_ptr()))
+            p1.record()
+            torch.cuda.synchronize()
+            best = max(best, probe_flops[0] / (p0.elapsed_time(p1) * 1e-3) / 1e12)
+        achieved = flops / (k_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = B * (4 * K + 2 * 16 * D + 4)  # counts in, start state in, state out, iteration count out
+        roof = {"kernel": "k_mle_rrr_small" if n <= 2 else "k_mle_rrr_generic", "bound": "fp64",
+                "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best if best else None,
+                "peak_source": "qpb_fp64_fma_probe, measured in this run (MEASURED_PEAKS.json has no FP64 line)",
+                "kernel_ms": k_ms, "flops_per_launch": flops, "mean_iterations": tot_iters / B,
+                "traffic": None,
+                "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",
+                        "note": "structurally tiny: the iteration never touches HBM"}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import state as ostate
+
+        cpu = cpu_baseline(args, centre, ostate.measurement_matrix(args.povm, n), n_meas)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clock_info, "gpu_launches": launches,
+                "mean_mle_iterations": mean_iters,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "steps": e2e_steps, "api": "quantpy_b200.BootstrapStateInterval(...).setup() + cl_to_dist"},
+                "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

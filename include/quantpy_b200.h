@@ -44,6 +44,10 @@ QPB_API const char* qpb_last_error(void);
 QPB_API int64_t qpb_launch_count(void);
 QPB_API void qpb_reset_launch_count(void);
 
+/* Roofline probe (bench.py only): runs a pure FP64 FMA kernel on every SM; *flops_out_host receives the
+ * number of floating-point operations it performs so that the caller can time it with CUDA events. */
+QPB_API int qpb_fp64_fma_probe(int64_t iters_per_thread, double* sink, double* flops_out_host, void* stream);
+
 /* ---- state plan ---------------------------------------------------------------------------
  * Device-resident operator tables for one (POVM, shot vector) pair, hoisted out of the
  * per-sample loop.  Inputs are exactly the reference's intermediates:

@@ -33,6 +33,7 @@ SIGNATURES = {
     "qpb_last_error": (ctypes.c_char_p, []),
     "qpb_launch_count": (ctypes.c_int64, []),
     "qpb_reset_launch_count": (None, []),
+    "qpb_fp64_fma_probe": (_int, [ctypes.c_int64, _vp, ctypes.POINTER(_dbl), _vp]),
     "qpb_state_plan_create": (_int, [ctypes.POINTER(_vp), _int, _int, _vp, _vp, _vp]),
     "qpb_state_plan_destroy": (_int, [_vp]),
     "qpb_povm_probs": (_int, [_int, _int, _int, _vp, _vp, _dbl, _int, _vp, _vp]),

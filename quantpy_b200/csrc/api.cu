@@ -36,7 +36,32 @@ int num_sms() {
 
 }  // namespace qpb
 
+namespace qpb {
+// Roofline probe: 8 independent FMA chains per thread, nothing else.  bench.py times it with CUDA
+// events to get the FP64 FMA peak of the device it is running on (MEASURED_PEAKS.json has no FP64 line).
+__global__ void k_fp64_fma_probe(long iters, double seed, double* __restrict__ sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (long i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.6789) sink[0] = s;  // never true; keeps the chains alive
+}
+}  // namespace qpb
+
 extern "C" {
+
+int qpb_fp64_fma_probe(int64_t iters_per_thread, double* sink, double* flops_out_host, void* stream) {
+    QPB_REQUIRE(iters_per_thread > 0 && sink != nullptr, "bad probe arguments");
+    const int blocks = qpb::num_sms() * 8, threads = 256;
+    qpb::k_fp64_fma_probe<<<blocks, threads, 0, (cudaStream_t)stream>>>((long)iters_per_thread, 1.0, sink);
+    QPB_LAUNCHED("k_fp64_fma_probe");
+    if (flops_out_host) *flops_out_host = 2.0 * 8.0 * (double)iters_per_thread * blocks * threads;
+    return QPB_OK;
+}
 
 int qpb_abi_version(void) { return QPB_ABI_VERSION; }
 const char* qpb_last_error(void) { return qpb::g_err; }

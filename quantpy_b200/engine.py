@@ -129,29 +129,45 @@ class StatePlan:
             return self.mle(counts, start, max_iter, tol)
         raise ValueError("Invalid value for argument `method`")
 
-    def bootstrap(self, probs, n_samples, seed, offset, ref_matrix, method="lin", physical=True, init="lin",
-                  max_iter=100, tol=1e-3, dst="hs", keep=False):
-        """Fused bootstrap (interval.py:598-609) -> dict of device tensors: dist (+ rho, counts, iters)."""
+    def bootstrap_buffers(self, n_samples, keep=False):
+        """Device buffers for `bootstrap_into` (allocate once, reuse across calls)."""
         torch = nt.torch_cuda()
+        B = int(n_samples)
+        nbytes = self._lib.qpb_bootstrap_state_workspace(self.handle, B, self.P, self.O)
+        return {
+            "dist": torch.empty((B,), dtype=torch.float64, device="cuda"),
+            "counts": torch.empty((B, self.P, self.O), dtype=torch.int32, device="cuda"),
+            "iters": torch.empty((B,), dtype=torch.int32, device="cuda"),
+            "rho": torch.empty((B, self.d, self.d, 2), dtype=torch.float64, device="cuda") if keep else None,
+            "work": torch.empty((max(int(nbytes), 8),), dtype=torch.uint8, device="cuda"),
+        }
+
+    def bootstrap_into(self, bufs, probs, ref, seed, offset, method="lin", physical=True, init="lin",
+                       max_iter=100, tol=1e-3, dst="hs"):
+        """qpb_bootstrap_state on device-resident inputs (probs [K], ref [d, d, 2]) into `bufs`.
+        Asynchronous: nothing is copied to or from the host."""
         if method not in nt.METHODS:
             raise ValueError("Invalid value for argument `method`")
         if init not in nt.INITS:
             raise ValueError("Invalid value for argument `init`")
-        B = int(n_samples)
-        ref = nt.complex_to_device(ref_matrix)
-        dist = torch.empty((B,), dtype=torch.float64, device="cuda")
-        counts = torch.empty((B, self.P, self.O), dtype=torch.int32, device="cuda")
-        iters = torch.empty((B,), dtype=torch.int32, device="cuda")
-        rho = torch.empty((B, self.d, self.d, 2), dtype=torch.float64, device="cuda") if keep else None
-        nbytes = self._lib.qpb_bootstrap_state_workspace(self.handle, B, self.P, self.O)
-        work = torch.empty((max(int(nbytes), 8),), dtype=torch.uint8, device="cuda")
+        B = bufs["dist"].shape[0]
         shots = np.ascontiguousarray(self.n_shots)
         nt.check(self._lib.qpb_bootstrap_state(
-            self.handle, B, self.P, self.O, nt.ptr(probs.contiguous()), shots.ctypes.data_as(ctypes.c_void_p),
+            self.handle, B, self.P, self.O, nt.ptr(probs), shots.ctypes.data_as(ctypes.c_void_p),
             ctypes.c_uint64(seed), ctypes.c_uint64(offset), nt.METHODS[method], int(bool(physical)),
-            nt.INITS[init], int(max_iter), float(tol), nt.ptr(ref), nt.DIST_KINDS[dst], nt.ptr(dist),
-            nt.ptr(rho), nt.ptr(counts), nt.ptr(iters), nt.ptr(work), nt.stream_ptr()))
-        return {"dist": dist, "rho": rho, "counts": counts, "iters": iters, "_keepalive": (work, ref)}
+            nt.INITS[init], int(max_iter), float(tol), nt.ptr(ref), nt.DIST_KINDS[dst], nt.ptr(bufs["dist"]),
+            nt.ptr(bufs["rho"]), nt.ptr(bufs["counts"]), nt.ptr(bufs["iters"]), nt.ptr(bufs["work"]),
+            nt.stream_ptr()))
+        return bufs
+
+    def bootstrap(self, probs, n_samples, seed, offset, ref_matrix, method="lin", physical=True, init="lin",
+                  max_iter=100, tol=1e-3, dst="hs", keep=False):
+        """Fused bootstrap (interval.py:598-609) -> dict of device tensors: dist, counts, iters (+ rho)."""
+        bufs = self.bootstrap_buffers(n_samples, keep)
+        ref = nt.complex_to_device(ref_matrix)
+        self.bootstrap_into(bufs, probs.contiguous(), ref, seed, offset, method, physical, init, max_iter, tol, dst)
+        bufs["_keepalive"] = ref
+        return bufs
 
 
 def distance(rho, ref_matrix, dst="hs"):

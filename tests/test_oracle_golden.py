@@ -12,6 +12,14 @@ STATE_CASES = ["state_c1", "state_c1_pure", "state_c2", "state_c2_set", "state_c
                "state_c2_sic", "state_c3", "state_c3_rank2", "state_c4"]
 
 
+def sqrtm_tolerances(est, rho):
+    """Per-sample tolerance against sqrtm-based reference distances: 1e-10 when all spectra are
+    regular, 1e-6 when one of them is within 1e-6 of singular (the reference itself is noisy there)."""
+    gap_tr = np.abs(np.linalg.eigvalsh(est - rho)).min(-1)
+    gap_if = np.minimum(np.linalg.eigvalsh(est).min(-1), np.linalg.eigvalsh(rho).min())
+    return np.where(gap_tr > 1e-6, 1e-10, 1e-6), np.where(gap_if > 1e-6, 1e-10, 1e-6)
+
+
 def fro(a, b):
     return np.sqrt(np.sum(np.abs(np.asarray(a) - np.asarray(b)) ** 2, axis=(-2, -1)))
 
@@ -52,11 +60,14 @@ def test_distances(golden, case):
     g = golden(case)
     rho = g["rho_true"]
     est = g["lin_physical"]
-    assert np.allclose(odist.hs(est, rho), g["dist_hs"], atol=1e-14)
-    assert np.allclose(odist.trace(est, rho), g["dist_trace"], atol=1e-12)
-    # sqrtm of a matrix with eigenvalues clipped to 1e-15 is itself only ~1e-8 accurate
-    tol = 1e-7 if case.endswith(("pure", "rank1", "rank2")) else 1e-10
-    assert np.allclose(odist.infidelity(est, rho), g["dist_if"], atol=tol)
+    assert np.abs(odist.hs(est, rho) - g["dist_hs"]).max() < 1e-14
+    # The reference evaluates trace/infidelity through scipy.linalg.sqrtm, which loses accuracy
+    # (~sqrt(eps)) when its argument is numerically singular: est has eigenvalues clipped to 1e-15
+    # whenever the raw estimate was not positive, and est - rho can have a ~1e-16 eigenvalue.
+    # Where every spectrum involved is well away from zero the forms agree to 1e-10.
+    tol_tr, tol_if = sqrtm_tolerances(est, rho)
+    assert (np.abs(odist.trace(est, rho) - g["dist_trace"]) < tol_tr).all()
+    assert (np.abs(odist.infidelity(est, rho) - g["dist_if"]) < tol_if).all()
 
 
 def test_distance_literal_forms(golden):
