@@ -2,6 +2,9 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "../../include/quantpy_b200.h"
 #include "common.cuh"
@@ -22,6 +25,29 @@ int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return QPB_OK;
     set_error("CUDA error %s (%d) in %s", cudaGetErrorString(e), (int)e, what);
     return QPB_ERR_CUDA;
+}
+
+void* scratch(cudaStream_t st, int slot, size_t bytes) {
+    struct Buf {
+        void* p = nullptr;
+        size_t n = 0;
+    };
+    static std::mutex mu;
+    static std::map<std::pair<cudaStream_t, int>, Buf> pool;
+    std::lock_guard<std::mutex> lock(mu);
+    Buf& b = pool[std::make_pair(st, slot)];
+    if (b.n < bytes) {
+        if (b.p) {
+            cudaStreamSynchronize(st);  // earlier kernels on this stream may still read the old buffer
+            cudaFree(b.p);
+            b.p = nullptr;
+            b.n = 0;
+        }
+        size_t want = bytes < 4096 ? 4096 : bytes;
+        if (check_cuda(cudaMalloc(&b.p, want), "scratch cudaMalloc") != QPB_OK) return nullptr;
+        b.n = want;
+    }
+    return b.p;
 }
 
 int num_sms() {

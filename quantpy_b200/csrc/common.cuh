@@ -19,6 +19,11 @@ int check_cuda(cudaError_t e, const char* what);
 int num_sms();
 extern std::atomic<int64_t> g_launches;
 
+// Grow-only device scratch, one buffer per (stream, slot): kernels of one call reuse it in stream order, so no
+// allocation (and no allocator-induced gap after an idle period) happens on the hot path.  Returns nullptr
+// and sets the error on failure.
+void* scratch(cudaStream_t st, int slot, size_t bytes);
+
 // Call right after a <<<>>> launch: counts it and surfaces launch-configuration errors.
 #define QPB_LAUNCHED(name)                                     \
     do {                                                       \

@@ -8,6 +8,8 @@ struct qpb_state_plan {
     double* Ar = nullptr;   // [K][D] packed-Hermitian POVM operators
     double* ArT = nullptr;  // [D][K]
     double* LhT = nullptr;  // [K][D] packed-Hermitian linear-inversion map (NULL if no L given)
+    double* A_host = nullptr;   // host copy of the Bloch-basis table A [K][D] (structure detection)
+    double* Ar_host = nullptr;  // host copy of Ar for kernels that take the table as a launch parameter
 };
 
 struct qpb_process_plan {
@@ -20,6 +22,9 @@ namespace qpb {
 
 int launch_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts, int physical, double* rho,
                        cudaStream_t st);
+// Register-resident variant for n <= 2 (lin_small.cu); QPB_ERR_UNSUPPORTED otherwise.
+int launch_lin_project_small(const qpb_state_plan* plan, int B, const int32_t* counts, int physical, double* rho,
+                             cudaStream_t st);
 int launch_mle_generic(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                        double tol, double* rho, int32_t* iters, cudaStream_t st);
 int launch_distance(int d, int B, const double* rho, const double* ref, int kind, double* dist, cudaStream_t st);

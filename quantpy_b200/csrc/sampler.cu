@@ -162,9 +162,11 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
     int* stack = nullptr;
     if (!p_batched) {
         const size_t cells = (size_t)P * O;
-        QPB_CUDA(cudaMallocAsync(&tables, sizeof(uint2) * cells, st));
-        QPB_CUDA(cudaMallocAsync(&q, sizeof(double) * cells, st));
-        QPB_CUDA(cudaMallocAsync(&stack, sizeof(int) * cells, st));
+        unsigned char* base = static_cast<unsigned char*>(scratch(st, 1, (sizeof(uint2) + sizeof(double) + sizeof(int)) * cells + 64));
+        if (!base) return QPB_ERR_NOMEM;
+        q = reinterpret_cast<double*>(base);
+        tables = reinterpret_cast<uint2*>(q + cells);
+        stack = reinterpret_cast<int*>(tables + cells);
         k_alias_build<<<(P + 31) / 32, 32, 0, st>>>(p, P, O, q, stack, tables);
         QPB_LAUNCHED("k_alias_build");
     }
@@ -183,10 +185,5 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
     kern<<<(int)blocks, warps * 32, smem, st>>>(B, P, O, p, p_batched, tables, shots, (uint32_t)seed,
                                                 (uint32_t)(seed >> 32), offset, counts);
     QPB_LAUNCHED("k_multinomial");
-    if (!p_batched) {
-        QPB_CUDA(cudaFreeAsync(tables, st));
-        QPB_CUDA(cudaFreeAsync(q, st));
-        QPB_CUDA(cudaFreeAsync(stack, st));
-    }
     return QPB_OK;
 }

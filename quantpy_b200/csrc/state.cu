@@ -7,6 +7,7 @@
 //   LhT [K][D]  packed-Hermitian linear-inversion map: rho_hat(packed) = sum_k LhT[k][:] f_k
 //   counts [B][K] int32, rho [B][d][d] complex128 (row-major, (re,im) pairs)
 #include <cmath>
+#include <cstdlib>
 
 #include "../../include/quantpy_b200.h"
 #include "common.cuh"
@@ -496,12 +497,25 @@ int qpb_state_plan_create(qpb_state_plan** out, int n_qubits, int K, const doubl
         k_bloch_to_packed<<<grid, 256, 0, st>>>(L, K, 1, K, p->n, 1.0 / p->d, p->LhT, nullptr);
         QPB_LAUNCHED("k_bloch_to_packed(L)");
     }
+    if (p->n <= 2) {  // small tables also travel as kernel parameters (mle_small.cu)
+        p->Ar_host = new double[(size_t)K * p->D];
+        p->A_host = new double[(size_t)K * p->D];
+        rc = check_cuda(cudaMemcpyAsync(p->Ar_host, p->Ar, bytes, cudaMemcpyDeviceToHost, st), "copy Ar to host");
+        if (rc == QPB_OK) rc = check_cuda(cudaMemcpyAsync(p->A_host, A, bytes, cudaMemcpyDeviceToHost, st), "copy A to host");
+        if (rc == QPB_OK) rc = check_cuda(cudaStreamSynchronize(st), "plan sync");
+        if (rc != QPB_OK) {
+            qpb_state_plan_destroy(p);
+            return rc;
+        }
+    }
     *out = p;
     return QPB_OK;
 }
 
 int qpb_state_plan_destroy(qpb_state_plan* p) {
     if (!p) return QPB_OK;
+    delete[] p->Ar_host;
+    delete[] p->A_host;
     cudaFree(p->Ar);
     cudaFree(p->ArT);
     cudaFree(p->LhT);
@@ -527,7 +541,10 @@ int qpb_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts, in
     QPB_REQUIRE(B >= 0, "negative batch");
     if (B == 0) return QPB_OK;
     QPB_REQUIRE(counts && rho, "NULL buffer");
-    return launch_lin_project(plan, B, counts, physical, rho, (cudaStream_t)stream);
+    int rc = getenv("QPB_NO_LIN_SMALL") ? QPB_ERR_UNSUPPORTED
+                                        : launch_lin_project_small(plan, B, counts, physical, rho, (cudaStream_t)stream);
+    if (rc == QPB_ERR_UNSUPPORTED) rc = launch_lin_project(plan, B, counts, physical, rho, (cudaStream_t)stream);
+    return rc;
 }
 
 int qpb_distance(int dd, int B, const double* rho, const double* ref, int kind, double* dist, void* stream) {
