@@ -221,6 +221,17 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def traffic_from_profile(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel at this workload, from the
+    committed `ncu --set full` capture (profiles/traffic.json); None if no capture exists for the kernel."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except OSError:
+        return None
+    entry = table.get(kernel)
+    return entry["dram_bytes"] if entry else None
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -330,7 +341,18 @@ def run_ours(args, rank, local_rank, world):
         k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
         K, D, d = plan.K, plan.D, plan.d
         tot_iters = float(iters.double().sum().item())
-        flops = tot_iters * (4 * K * D + 16 * d**3) + 2.0 * K * D * B
+        variant = {0: "k_mle_rrr_generic", 1: "k_mle_rrr_small", 2: "k_mle_rrr_const", 3: "k_mle_rrr_pauli2"}[
+            int(lib.qpb_mle_variant(plan.handle))]
+        if variant == "k_mle_rrr_pauli2":
+            # structured contraction: 608 FMA + 344 add/mul per iteration, counted as executed
+            flop_iter, fp64_inst_iter = 2 * 641 + 311, 952
+            flop_note = ("executed flops of the structured (Pauli-axis) iteration: 641 DFMA + 269 DADD + 42 DMUL per "
+                         "iteration (ncu op counts, profiles/README_r1.md), FMA = 2 flop")
+        else:
+            flop_iter = 4 * K * D + 16 * d**3                                # SURVEY section 8d, dense contraction
+            fp64_inst_iter = flop_iter // 2 + 5 * K
+            flop_note = "SURVEY 8d: 4KD + 16 d^3 flop per iteration"
+        flops = tot_iters * flop_iter
         # FP64 peak, measured now on this device
         sink = torch.zeros(8, dtype=torch.float64, device="cuda")
         probe_flops = np.zeros(1)
@@ -352,11 +374,15 @@ def run_ours(args, rank, local_rank, world):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = B * (4 * K + 2 * 16 * D + 4)  # counts in, start state in, state out, iteration count out
-        roof = {"kernel": "k_mle_rrr_small" if n <= 2 else "k_mle_rrr_generic", "bound": "fp64",
+        pipe_frac = tot_iters * fp64_inst_iter * 2.0 / (k_ms * 1e-3) / 1e12 / best if best else None
+        roof = {"kernel": variant, "bound": "fp64",
                 "achieved": achieved, "peak": best, "unit": "TFLOP/s", "frac": achieved / best if best else None,
+                "flop_per_iteration": flop_iter, "flop_note": flop_note,
+                "fp64_pipe_frac": pipe_frac,
+                "fp64_pipe_note": "FP64 instructions issued (FMA, add, mul each occupy one pipe slot) / probe's FMA rate",
                 "peak_source": "qpb_fp64_fma_probe, measured in this run (MEASURED_PEAKS.json has no FP64 line)",
                 "kernel_ms": k_ms, "flops_per_launch": flops, "mean_iterations": tot_iters / B,
-                "traffic": None,
+                "traffic": traffic_from_profile(variant),
                 "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback",

@@ -87,6 +87,12 @@ QPB_API int qpb_lin_project(const qpb_state_plan* plan, int B, const int32_t* co
 QPB_API int qpb_mle_rrr(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                 double tol, double* rho, int32_t* iters, void* stream);
 
+/* Which R.rho.R kernel qpb_mle_rrr dispatches to for this plan (bench.py uses it to count flops):
+ * GENERIC: warp per sample, any n<=4 | SMALL: thread per sample, table in shared memory |
+ * CONST: thread per sample, table in constant bank, unrolled | PAULI2: two-qubit Pauli-axis POVM, no table. */
+enum { QPB_MLE_GENERIC = 0, QPB_MLE_SMALL = 1, QPB_MLE_CONST = 2, QPB_MLE_PAULI2 = 3 };
+QPB_API int qpb_mle_variant(const qpb_state_plan* plan);
+
 /* k8: dist[b] = dst(rho[b], ref) with the reference's argument order dst(estimate, centre)
  * (interval.py:609) and its "below 1e-15 -> 0" rule.  dd is the matrix side (d or d^2 for Choi). */
 QPB_API int qpb_distance(int dd, int B, const double* rho, const double* ref, int kind, double* dist, void* stream);

@@ -40,6 +40,7 @@ SIGNATURES = {
     "qpb_multinomial": (_int, [_int, _int, _int, _vp, _int, _vp, _u64, _u64, _vp, _vp]),
     "qpb_lin_project": (_int, [_vp, _int, _vp, _int, _vp, _vp]),
     "qpb_mle_rrr": (_int, [_vp, _int, _vp, _vp, _int, _dbl, _vp, _vp, _vp]),
+    "qpb_mle_variant": (_int, [_vp]),
     "qpb_distance": (_int, [_int, _int, _vp, _vp, _int, _vp, _vp]),
     "qpb_bootstrap_state_workspace": (ctypes.c_size_t, [_vp, _int, _int, _int]),
     "qpb_bootstrap_state": (_int, [_vp, _int, _int, _int, _vp, _vp, _u64, _u64, _int, _int, _int, _int, _dbl,

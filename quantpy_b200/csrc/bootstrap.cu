@@ -23,6 +23,11 @@ int qpb_mle_rrr(const qpb_state_plan* plan, int B, const int32_t* counts, const 
     return rc;
 }
 
+int qpb_mle_variant(const qpb_state_plan* plan) {
+    QPB_REQUIRE(plan != nullptr, "plan is NULL");
+    return mle_variant(plan);
+}
+
 size_t qpb_bootstrap_state_workspace(const qpb_state_plan* plan, int B, int P, int O) {
     if (!plan || B <= 0) return 0;
     (void)P;

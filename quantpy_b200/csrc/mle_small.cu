@@ -647,6 +647,21 @@ static bool detect_pauli2(const double* A, int K, PauliParams* pp) {
     return true;
 }
 
+// Which kernel qpb_mle_rrr will run for this plan (also exported through qpb_mle_variant for bench.py).
+int mle_variant(const qpb_state_plan* plan) {
+    if (plan->n > 2) return QPB_MLE_GENERIC;
+    if (plan->n == 2 && plan->A_host && !getenv("QPB_NO_PAULI_KERNEL")) {
+        PauliParams pp;
+        if (detect_pauli2(plan->A_host, plan->K, &pp)) return QPB_MLE_PAULI2;
+    }
+    if (plan->Ar_host && !getenv("QPB_NO_CONST_KERNEL")) {
+        if ((plan->n == 2 && (plan->K == 36 || plan->K == 16)) || (plan->n == 1 && (plan->K == 6 || plan->K == 4)))
+            return QPB_MLE_CONST;
+    }
+    const size_t smem = sizeof(double) * ((size_t)plan->K * plan->D + (size_t)plan->K * kSmallThreads);
+    return smem > 200 * 1024 ? QPB_MLE_GENERIC : QPB_MLE_SMALL;
+}
+
 int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                      double tol, double* rho, int32_t* iters, cudaStream_t st) {
     if (plan->n > 2) return QPB_ERR_UNSUPPORTED;

@@ -33,4 +33,6 @@ int launch_distance(int d, int B, const double* rho, const double* ref, int kind
 int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                      double tol, double* rho, int32_t* iters, cudaStream_t st);
 
+int mle_variant(const qpb_state_plan* plan);
+
 }  // namespace qpb

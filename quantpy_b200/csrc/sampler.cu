@@ -13,6 +13,8 @@
 #include "../../include/quantpy_b200.h"
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace qpb {
 
 constexpr int kMaxPovms = 256;
@@ -141,6 +143,167 @@ __global__ void k_multinomial(int B, int P, int O, const double* __restrict__ p,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Conditional-binomial multinomial: counts_o ~ Binomial(n_left, p_o / p_left) for o = 0..O-2, the last
+// outcome takes what is left -- the decomposition NumPy's multinomial uses (state.py:112), so the work per
+// resample is O(O) instead of O(shots).  One thread per (resample, POVM).
+// Binomial variates are exact: sequential inversion (BINV) when n*min(p,1-p) < 30, otherwise the BTPE
+// triangle/parallelogram/exponential-tail rejection scheme of Kachitvichyanukul & Schmeiser, "Binomial
+// random variate generation", CACM 31 (1988), with its squeeze and Stirling-series final test.
+// Uniforms are 53-bit, strictly inside (0,1), two per Philox4x32-10 block.
+// ------------------------------------------------------------------------------------------------
+struct PhiloxStream {
+    uint32_t k0, k1, c1, c2, c3, j;
+    double spare;
+    bool have;
+    __device__ __forceinline__ double next() {
+        if (have) {
+            have = false;
+            return spare;
+        }
+        const philox4 r = philox4x32_10(j++, c1, c2, c3, k0, k1);
+        const double scale = 1.0 / 9007199254740992.0;  // 2^-53
+        spare = ((double)(((uint64_t)(r.z >> 5) << 26) | (uint64_t)(r.w >> 6)) + 0.5) * scale;
+        have = true;
+        return ((double)(((uint64_t)(r.x >> 5) << 26) | (uint64_t)(r.y >> 6)) + 0.5) * scale;
+    }
+};
+
+__device__ __forceinline__ double stirling_tail(double x, double x2) {
+    return (13860.0 - (462.0 - (132.0 - (99.0 - 140.0 / x2) / x2) / x2) / x2) / x / 166320.0;
+}
+
+// Binomial(n, p) for 0 < p <= 0.5 and n*p >= 30.
+__device__ long binomial_btpe(long n, double r, PhiloxStream& rng) {
+    const double q = 1.0 - r;
+    const double nrq = (double)n * r * q;
+    const double fm = (double)n * r + r;
+    const long M = (long)floor(fm);
+    const double p1 = floor(2.195 * sqrt(nrq) - 4.6 * q) + 0.5;
+    const double xm = (double)M + 0.5, xl = xm - p1, xr = xm + p1;
+    const double c = 0.134 + 20.5 / (15.3 + (double)M);
+    double a = (fm - xl) / (fm - xl * r);
+    const double laml = a * (1.0 + 0.5 * a);
+    a = (xr - fm) / (xr * q);
+    const double lamr = a * (1.0 + 0.5 * a);
+    const double p2 = p1 * (1.0 + 2.0 * c);
+    const double p3 = p2 + c / laml;
+    const double p4 = p3 + c / lamr;
+    for (;;) {
+        const double u = rng.next() * p4;
+        double v = rng.next();
+        long y;
+        if (u <= p1) {  // triangle: always accepted
+            return (long)floor(xm - p1 * v + u);
+        } else if (u <= p2) {  // parallelograms
+            const double x = xl + (u - p1) / c;
+            v = v * c + 1.0 - fabs((double)M - x + 0.5) / p1;
+            if (v > 1.0) continue;
+            y = (long)floor(x);
+        } else if (u <= p3) {  // left exponential tail
+            y = (long)floor(xl + log(v) / laml);
+            if (y < 0) continue;
+            v = v * (u - p2) * laml;
+        } else {  // right exponential tail
+            y = (long)floor(xr - log(v) / lamr);
+            if (y > n) continue;
+            v = v * (u - p3) * lamr;
+        }
+        const long k = labs(y - M);
+        if (k <= 20 || (double)k >= 0.5 * nrq - 1.0) {
+            // evaluate f(y)/f(M) by the recurrence
+            const double s = r / q, aa = s * (double)(n + 1);
+            double F = 1.0;
+            if (M < y) {
+                for (long i = M + 1; i <= y; ++i) F *= (aa / (double)i - s);
+            } else if (M > y) {
+                for (long i = y + 1; i <= M; ++i) F /= (aa / (double)i - s);
+            }
+            if (v > F) continue;
+            return y;
+        }
+        // squeeze on log f(y)/f(M)
+        const double kd = (double)k;
+        const double rho = (kd / nrq) * ((kd * (kd / 3.0 + 0.625) + 0.1666666666666) / nrq + 0.5);
+        const double t = -kd * kd / (2.0 * nrq);
+        const double A = log(v);
+        if (A < t - rho) return y;
+        if (A > t + rho) continue;
+        const double x1 = (double)(y + 1), f1 = (double)(M + 1), z = (double)(n + 1 - M), w = (double)(n - y + 1);
+        const double bound = xm * log(f1 / x1) + ((double)(n - M) + 0.5) * log(z / w) +
+                             (double)(y - M) * log(w * r / (x1 * q)) + stirling_tail(f1, f1 * f1) +
+                             stirling_tail(z, z * z) + stirling_tail(x1, x1 * x1) + stirling_tail(w, w * w);
+        if (A > bound) continue;
+        return y;
+    }
+}
+
+// Binomial(n, p) for 0 < p <= 0.5 and n*p < 30: sequential search from 0 (BINV).
+__device__ long binomial_inversion(long n, double p, PhiloxStream& rng) {
+    const double q = 1.0 - p;
+    const double s = p / q, a = (double)(n + 1) * s;
+    const double r0 = exp((double)n * log(q));
+    for (;;) {
+        double u = rng.next(), r = r0;
+        long x = 0;
+        bool ok = true;
+        while (u > r) {
+            u -= r;
+            ++x;
+            if (x > n || x > 200) {  // unreachable but for accumulated rounding in the tail: redraw
+                ok = false;
+                break;
+            }
+            r *= (a / (double)x - s);
+        }
+        if (ok) return x;
+    }
+}
+
+__device__ __forceinline__ long binomial_draw(long n, double p, PhiloxStream& rng) {
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    const bool flip = p > 0.5;
+    const double r = flip ? 1.0 - p : p;
+    long y;
+    if (!(r > 0.0)) y = 0;
+    else if ((double)n * r < 30.0) y = binomial_inversion(n, r, rng);
+    else y = binomial_btpe(n, r, rng);
+    return flip ? n - y : y;
+}
+
+__global__ void k_multinomial_binomial(int B, int P, int O, const double* __restrict__ p, int batched, ShotVec shots,
+                                       uint32_t k0, uint32_t k1, uint64_t offset, int32_t* __restrict__ counts) {
+    const long items = (long)B * P;
+    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
+        const long b = item / P;
+        const int m = (int)(item % P);
+        const double* row = p + (batched ? item : (long)m) * O;
+        const uint64_t sample = offset + (uint64_t)b;
+        PhiloxStream rng;
+        rng.k0 = k0; rng.k1 = k1;
+        rng.c1 = (uint32_t)m | 0x80000000u;  // separate counter domain from the alias sampler
+        rng.c2 = (uint32_t)sample; rng.c3 = (uint32_t)(sample >> 32);
+        rng.j = 0; rng.have = false; rng.spare = 0.0;
+        long left = shots.n[m];
+        double mass = 1.0;
+        int32_t* out = counts + item * O;
+        for (int o = 0; o + 1 < O; ++o) {
+            const double po = fmin(fmax(row[o], 0.0), 1.0);
+            long c = 0;
+            if (left > 0 && po > 0.0) {
+                const double cond = mass > 0.0 ? fmin(po / mass, 1.0) : 1.0;
+                c = binomial_draw(left, cond, rng);
+            }
+            out[o] = (int32_t)c;
+            left -= c;
+            mass -= po;
+        }
+        out[O - 1] = (int32_t)left;
+    }
+}
+
 }  // namespace qpb
 
 using namespace qpb;
@@ -156,6 +319,24 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
     for (int m = 0; m < P; ++m) {
         QPB_REQUIRE(n_shots_host[m] >= 0, "negative shot count");
         shots.n[m] = n_shots_host[m];
+    }
+    // O(O) conditional binomials beat O(shots) alias draws unless there are very few shots per outcome
+    long max_shots = 0;
+    for (int m = 0; m < P; ++m) max_shots = shots.n[m] > max_shots ? shots.n[m] : max_shots;
+    const char* force = getenv("QPB_SAMPLER");
+    bool use_binomial = max_shots > 4L * O;
+    if (force && force[0] == 'a') use_binomial = false;
+    if (force && force[0] == 'b') use_binomial = true;
+    if (use_binomial) {
+        const long items = (long)B * P;
+        const int threads = 128;
+        long blocks = (items + threads - 1) / threads;
+        const long cap = (long)num_sms() * 16;
+        if (blocks > cap) blocks = cap;
+        k_multinomial_binomial<<<(int)blocks, threads, 0, st>>>(B, P, O, p, p_batched, shots, (uint32_t)seed,
+                                                               (uint32_t)(seed >> 32), offset, counts);
+        QPB_LAUNCHED("k_multinomial_binomial");
+        return QPB_OK;
     }
     uint2* tables = nullptr;
     double* q = nullptr;

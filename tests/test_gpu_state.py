@@ -55,8 +55,47 @@ def test_probabilities_match_reference(qp, golden, case):
     assert np.abs(p - g["probs"]).max() < 1e-14
 
 
+@pytest.fixture(params=["binomial", "alias"])
+def sampler_kind(request, monkeypatch):
+    """Both multinomial kernels are held to the same distributional tests (QPB_SAMPLER forces one)."""
+    monkeypatch.setenv("QPB_SAMPLER", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("n_shots,p", [(10000, 0.3), (10000, 1 / 36), (10000, 0.001), (10000, 0.9995), (100, 0.5),
+                                       (57, 0.93), (1000000, 0.41), (3, 0.2), (2000, 0.015), (500, 0.06)])
+def test_binomial_kernel_matches_exact_pmf(qp, monkeypatch, n_shots, p):
+    """O = 2 makes the multinomial a single binomial draw: chi-square against scipy.stats.binom over
+    both regimes (inversion for n*min(p,1-p) < 30, BTPE otherwise) and the p > 1/2 reflection."""
+    import torch
+    from scipy import stats
+
+    from quantpy_b200 import engine
+
+    monkeypatch.setenv("QPB_SAMPLER", "binomial")
+    B = 400000
+    probs = torch.tensor([p, 1 - p], dtype=torch.float64, device="cuda")
+    counts = engine.sample_counts(probs, B, 1, 2, [n_shots], seed=7 + n_shots, offset=0).cpu().numpy()[:, 0, :]
+    assert (counts.sum(-1) == n_shots).all()
+    x = counts[:, 0]
+    assert abs(x.mean() - n_shots * p) < 6 * np.sqrt(n_shots * p * (1 - p) / B)
+    assert abs(x.var() / (n_shots * p * (1 - p)) - 1) < 0.02
+    lo, hi = int(x.min()), int(x.max())
+    ks = np.arange(lo, hi + 1)
+    observed = np.bincount(x - lo, minlength=len(ks)).astype(float)
+    expected = stats.binom.pmf(ks, n_shots, p) * B
+    # merge the sparse tails into their neighbours so that every cell expects >= 10 draws
+    keep = expected >= 10
+    first, last = np.argmax(keep), len(keep) - 1 - np.argmax(keep[::-1])
+    obs = np.r_[observed[:first + 1].sum(), observed[first + 1:last], observed[last:].sum()]
+    exp = np.r_[stats.binom.cdf(ks[first], n_shots, p) * B, expected[first + 1:last],
+                stats.binom.sf(ks[last] - 1, n_shots, p) * B]
+    stat = ((obs - exp) ** 2 / exp).sum()
+    assert stats.chi2.sf(stat, len(obs) - 1) > 1e-4, (stat, len(obs))
+
+
 @pytest.mark.parametrize("n,povm", [(1, "proj-set"), (2, "proj"), (2, "proj-set"), (3, "proj"), (4, "proj")])
-def test_sampler_counts_sum_and_chi_square(qp, n, povm):
+def test_sampler_counts_sum_and_chi_square(qp, sampler_kind, n, povm):
     """Integer stage: every POVM's counts sum to the shot number exactly.  Distribution: chi-square per
     outcome against the exact probabilities (NumPy's stream is not reproduced)."""
     from scipy import stats
@@ -86,7 +125,22 @@ def test_sampler_counts_sum_and_chi_square(qp, n, povm):
     assert abs(var / (shots * pk * (1 - pk)) - 1) < (0.15 if n < 4 else 0.4)
 
 
-def test_sampler_is_shard_invariant_and_seeded(qp):
+def test_multinomial_covariance(qp, sampler_kind):
+    """Joint structure: Cov(n_i, n_j) = -N p_i p_j for the conditional-binomial chain and the alias sampler."""
+    import torch
+
+    from quantpy_b200 import engine
+
+    p = np.array([0.5, 0.2, 0.15, 0.1, 0.05])
+    N, B = 5000, 200000
+    counts = engine.sample_counts(torch.tensor(p, device="cuda"), B, 1, 5, [N], seed=3).cpu().numpy()[:, 0, :].astype(float)
+    cov = np.cov(counts.T)
+    want = N * (np.diag(p) - np.outer(p, p))
+    assert np.abs(cov - want).max() < 0.03 * N * p.max()
+    assert np.abs(counts.mean(0) - N * p).max() < 0.2
+
+
+def test_sampler_is_shard_invariant_and_seeded(qp, sampler_kind):
     """The draw for a global sample index does not depend on the batch split (multi-GPU sharding)."""
     tmg = qp.StateTomograph(qp.Qobj(haar(2, 3)))
     full = tmg.sample_counts(64, 10000, "proj", seed=99)
@@ -102,7 +156,7 @@ def test_sampler_is_shard_invariant_and_seeded(qp):
     assert np.array_equal(x, y)
 
 
-def test_sampler_edge_cases(qp):
+def test_sampler_edge_cases(qp, sampler_kind):
     # a pure |0> state: z- outcome has probability exactly 0 and must never appear
     tmg = qp.StateTomograph(qp.Qobj([1, 0], is_ket=True))
     counts = tmg.sample_counts(500, [7, 1, 12345], "proj-set", seed=1)
