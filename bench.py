@@ -341,7 +341,7 @@ def run_ours(args, rank, local_rank, world):
         k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in kev]))
         K, D, d = plan.K, plan.D, plan.d
         tot_iters = float(iters.double().sum().item())
-        variant = {0: "k_mle_rrr_generic", 1: "k_mle_rrr_small", 2: "k_mle_rrr_const", 3: "k_mle_rrr_pauli2"}[
+        variant = {0: "k_mle_rrr_generic", 1: "k_mle_rrr_small", 2: "k_mle_rrr_const", 3: "k_mle_rrr_pauli2", 4: "k_mle_rrr_axis"}[
             int(lib.qpb_mle_variant(plan.handle))]
         if variant == "k_mle_rrr_pauli2":
             # structured contraction: 608 FMA + 344 add/mul per iteration, counted as executed

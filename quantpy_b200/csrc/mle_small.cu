@@ -649,7 +649,7 @@ static bool detect_pauli2(const double* A, int K, PauliParams* pp) {
 
 // Which kernel qpb_mle_rrr will run for this plan (also exported through qpb_mle_variant for bench.py).
 int mle_variant(const qpb_state_plan* plan) {
-    if (plan->n > 2) return QPB_MLE_GENERIC;
+    if (plan->n > 2) return (plan->axis_ok && !getenv("QPB_NO_AXIS_KERNEL")) ? QPB_MLE_AXIS : QPB_MLE_GENERIC;
     if (plan->n == 2 && plan->A_host && !getenv("QPB_NO_PAULI_KERNEL")) {
         PauliParams pp;
         if (detect_pauli2(plan->A_host, plan->K, &pp)) return QPB_MLE_PAULI2;

@@ -9,7 +9,11 @@ struct qpb_state_plan {
     double* ArT = nullptr;  // [D][K]
     double* LhT = nullptr;  // [K][D] packed-Hermitian linear-inversion map (NULL if no L given)
     double* A_host = nullptr;   // host copy of the Bloch-basis table A [K][D] (structure detection)
-    double* Ar_host = nullptr;  // host copy of Ar for kernels that take the table as a launch parameter
+    double* Ar_host = nullptr;
+    // n = 3, 4 Pauli-axis structure (mle_axis.cu): canonical slot of every count column, 1e-10/c per slot
+    bool axis_ok = false;
+    int* axis_slots = nullptr;
+    double* axis_epsp = nullptr;  // host copy of Ar for kernels that take the table as a launch parameter
 };
 
 struct qpb_process_plan {
@@ -34,5 +38,8 @@ int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, c
                      double tol, double* rho, int32_t* iters, cudaStream_t st);
 
 int mle_variant(const qpb_state_plan* plan);
+int axis_plan_setup(qpb_state_plan* plan, const double* A_host);
+int launch_mle_axis(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
+                    double tol, double* rho, int32_t* iters, cudaStream_t st);
 
 }  // namespace qpb

@@ -508,12 +508,25 @@ int qpb_state_plan_create(qpb_state_plan** out, int n_qubits, int K, const doubl
             return rc;
         }
     }
+    if (p->n >= 3) {  // structure detection for the axis kernel needs the Bloch-basis table on the host once
+        double* tmp = new double[(size_t)K * p->D];
+        rc = check_cuda(cudaMemcpyAsync(tmp, A, bytes, cudaMemcpyDeviceToHost, st), "copy A to host");
+        if (rc == QPB_OK) rc = check_cuda(cudaStreamSynchronize(st), "plan sync");
+        if (rc == QPB_OK) rc = axis_plan_setup(p, tmp);
+        delete[] tmp;
+        if (rc != QPB_OK) {
+            qpb_state_plan_destroy(p);
+            return rc;
+        }
+    }
     *out = p;
     return QPB_OK;
 }
 
 int qpb_state_plan_destroy(qpb_state_plan* p) {
     if (!p) return QPB_OK;
+    cudaFree(p->axis_slots);
+    cudaFree(p->axis_epsp);
     delete[] p->Ar_host;
     delete[] p->A_host;
     cudaFree(p->Ar);

@@ -60,9 +60,11 @@ def all_gather_concat(local, n_total):
     return torch.cat(pieces)
 
 
-def quantile_function(dist_values):
+def quantile_function(dist_values, presorted=False):
     """Sorted distances -> interp1d(linspace(0, 1, N), dist) as quantpy/tomography/interval.py:610-612."""
     from scipy.interpolate import interp1d
 
-    ordered = np.sort(np.asarray(dist_values, dtype=np.float64))
-    return interp1d(np.linspace(0, 1, len(ordered)), ordered)
+    ordered = np.asarray(dist_values, dtype=np.float64)
+    if not presorted:
+        ordered = np.sort(ordered)
+    return interp1d(np.linspace(0, 1, len(ordered)), ordered, assume_sorted=True)

@@ -238,6 +238,55 @@ def test_mle_tolerance_mode_matches_oracle(qp, n, povm, B, tol, max_iter):
     assert 1 <= its.mean() < max_iter
 
 
+@pytest.mark.parametrize("n,povm,disable,expect", [
+    (2, "proj", [], 3), (2, "proj", ["PAULI"], 2), (2, "proj", ["PAULI", "CONST"], 1),
+    (2, "proj-set", [], 3), (2, "proj4", [], 3), (2, "sic", [], 2), (2, "sic", ["CONST"], 1),
+    (1, "proj-set", [], 2), (1, "proj-set", ["CONST"], 1),
+    (3, "proj", [], 4), (3, "proj", ["AXIS"], 0), (3, "proj-set", [], 4), (3, "sic", [], 0), (4, "proj", [], 4),
+])
+def test_every_mle_kernel_variant_matches_oracle(qp, monkeypatch, n, povm, disable, expect):
+    """qpb_mle_rrr dispatches on the POVM's structure; every variant is the same update to 1e-10."""
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    for name in disable:
+        monkeypatch.setenv(f"QPB_NO_{name}_KERNEL", "1")
+    rho = haar(n, 90 + n, rank=2 if n == 3 else None)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(n)
+    tmg.experiment(10000, povm)
+    plan = engine.state_plan(tmg.povm_matrix, tmg.n_measurements)
+    assert nt.load_library().qpb_mle_variant(plan.handle) == expect
+    B = {1: 500, 2: 500, 3: 60, 4: 6}[n]
+    counts = tmg.sample_counts(B, 10000, povm, seed=17)
+    tol, max_iter = (1e-5, 40) if n < 4 else (0.0, 4)
+    got, its = tmg.point_estimate_batch(counts, "mle", max_iter=max_iter, tol=tol, return_iters=True)
+    want, wits = ostate.mle_rrr(counts, tmg.povm_matrix, tmg.n_measurements, max_iter=max_iter, tol=tol,
+                                return_iters=True)
+    assert np.array_equal(its, wits)
+    assert fro(got, want).max() < 1e-10
+    mixed = tmg.point_estimate_batch(counts[:4], "mle", init="mixed", max_iter=5, tol=0.0)
+    assert fro(mixed, ostate.mle_rrr(counts[:4], tmg.povm_matrix, tmg.n_measurements, init="mixed", max_iter=5,
+                                     tol=0.0)).max() < 1e-10
+
+
+def test_mle_with_unequal_shots_per_povm(qp):
+    """Shot weights enter the POVM table (state.py:193-196); the structured kernels carry them as per-slot guards."""
+    for n in (2, 3):
+        rho = haar(n, 7)
+        tmg = qp.StateTomograph(qp.Qobj(rho))
+        shots = (np.arange(3**n) % 4 + 1) * 2500
+        np.random.seed(1)
+        tmg.experiment(shots, "proj-set")
+        assert np.array_equal(tmg.results.sum(-1), shots)
+        counts = tmg.sample_counts(20, shots, "proj-set", seed=2)
+        got = tmg.point_estimate_batch(counts, "mle", max_iter=30, tol=0.0)
+        want = ostate.mle_rrr(counts, tmg.povm_matrix, tmg.n_measurements, max_iter=30, tol=0.0)
+        assert fro(got, want).max() < 1e-10
+        lin = tmg.point_estimate_batch(counts, "lin")
+        assert fro(lin, ostate.lin_estimate(counts, tmg.povm_matrix, tmg.n_measurements)).max() < 1e-10
+
+
 @pytest.mark.parametrize("case", ["state_c1", "state_c2", "state_c2_set", "state_c2_rank1", "state_c2_sic"])
 def test_mle_is_at_least_as_likely_as_reference(qp, golden, case):
     """Loose pin to the reference's BFGS 'mle' (SURVEY D1): our likelihood is never worse."""
