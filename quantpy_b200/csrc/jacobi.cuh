@@ -52,8 +52,8 @@ __device__ void warp_jacobi(cplx* __restrict__ A, cplx* __restrict__ V, jrot* __
         }
         off = warp_sum(off);
         fro = warp_sum(fro);
-        if (off <= 1e-33 * fro || fro == 0.0) break;
-        const double tiny2 = 1e-40 * fro;
+        if (off <= 1e-30 * fro || fro == 0.0) break;  // relative off-diagonal norm 1e-15: eigenvalues are second order in it
+        const double tiny2 = 1e-36 * fro;
         for (int round = 0; round < d - 1; ++round) {
             if (lane < half) {
                 int p, q;

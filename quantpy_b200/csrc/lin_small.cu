@@ -135,8 +135,8 @@ k_lin_project_small(int K, int B, const double* __restrict__ LhT, const int32_t*
                 fro += m2;
                 if (a != bb) off += m2;
             }
-        if (off <= 1e-33 * fro || fro == 0.0) break;
-        jacobi_sweep<d>(A, V, 1e-40 * fro);
+        if (off <= 1e-30 * fro || fro == 0.0) break;  // relative off-diagonal norm 1e-15: eigenvalues are second order in it
+        jacobi_sweep<d>(A, V, 1e-36 * fro);
     }
     double lam[d], tr = 0.0;
 #pragma unroll

@@ -22,7 +22,13 @@ namespace qpb {
 constexpr int kSmallThreads = 128;
 // The FP64 pipe saturates at a few warps per scheduler; fewer resident lanes also mean that more samples
 // flow through each lane (better balance) and that the straggler tail runs with less pipe sharing.
-constexpr int kMaxBlocksPerSm = 2;
+constexpr int kMaxBlocksPerSmDefault = 2;
+static int max_blocks_per_sm() {
+    const char* e = getenv("QPB_MLE_BLOCKS_PER_SM");
+    const int v = e ? atoi(e) : kMaxBlocksPerSmDefault;
+    return v < 1 ? 1 : v;
+}
+#define kMaxBlocksPerSm max_blocks_per_sm()
 
 template <int d>
 struct Packed {
@@ -472,6 +478,8 @@ struct PauliParams {
     int K;
 };
 
+__device__ int g_lane_limit = 32;  // experiment: lanes >= this never take samples
+
 __global__ void __launch_bounds__(kSmallThreads)
 k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* __restrict__ counts,
                  const double* __restrict__ rho0, int max_iter, double tol, double* __restrict__ rho,
@@ -486,7 +494,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
     double h[D];
     int it = 0;
     long b = -1;
-    bool alive = true;
+    bool alive = lane < g_lane_limit;
     const double tol2 = tol * tol;
 
     while (true) {
@@ -681,6 +689,10 @@ int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, c
             long blocks = (long)num_sms() * per_sm;
             const long need = ((long)B + kSmallThreads - 1) / kSmallThreads;
             if (blocks > need) blocks = need;
+            if (const char* e = getenv("QPB_LANE_LIMIT")) {
+                const int v = atoi(e);
+                cudaMemcpyToSymbolAsync(g_lane_limit, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st);
+            }
             k_mle_rrr_pauli2<<<(int)blocks, kSmallThreads, smem, st>>>(pp, B, counts, rho0, max_iter, tol, rho, iters,
                                                                       queue);
             QPB_LAUNCHED("k_mle_rrr_pauli2");

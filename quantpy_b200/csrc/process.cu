@@ -10,6 +10,8 @@
 #include "jacobi.cuh"
 #include "plan.h"
 
+#include <cstdlib>
+
 namespace qpb {
 
 // LinvT[col][r*s + c] = Linv[(c*s + r)][col]   (vec index = column stacking)
@@ -227,15 +229,22 @@ int qpb_lifp_cptp(const qpb_process_plan* plan, int B, const int32_t* counts, in
     QPB_REQUIRE(counts && choi, "NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const int cols = plan->S * plan->K;
-    const int warps = 8;
-    const size_t smem = sizeof(double) * (size_t)warps * cols;
-    QPB_REQUIRE(smem <= 200 * 1024, "S*K=%d too large", cols);
-    if (smem > 48 * 1024) QPB_CUDA(cudaFuncSetAttribute(k_lifp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long blocks = ((long)B + warps - 1) / warps;
-    const long cap = (long)num_sms() * 4;
-    if (blocks > cap) blocks = cap;
-    k_lifp<<<(int)blocks, warps * 32, smem, st>>>(plan->S, plan->K, plan->d4, B, plan->LinvT, counts, choi);
-    QPB_LAUNCHED("k_lifp");
+    if (!getenv("QPB_NO_DMMA_GEMM")) {
+        // choi [B][2 d^4] = freq [B][S*K] * LinvT [S*K][2 d^4], frequencies normalised per input state
+        int rc = launch_gemm_counts(B, 2 * plan->d4, cols, plan->K, counts, plan->LinvT, choi, st);
+        if (rc != QPB_OK) return rc;
+    } else {
+        const int warps = 8;
+        const size_t smem = sizeof(double) * (size_t)warps * cols;
+        QPB_REQUIRE(smem <= 200 * 1024, "S*K=%d too large", cols);
+        if (smem > 48 * 1024)
+            QPB_CUDA(cudaFuncSetAttribute(k_lifp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        long blocks = ((long)B + warps - 1) / warps;
+        const long cap = (long)num_sms() * 4;
+        if (blocks > cap) blocks = cap;
+        k_lifp<<<(int)blocks, warps * 32, smem, st>>>(plan->S, plan->K, plan->d4, B, plan->LinvT, counts, choi);
+        QPB_LAUNCHED("k_lifp");
+    }
     if (cptp) return launch_cptp(plan->n, B, choi, n_iter, tol, choi, iters, st);
     if (iters) QPB_CUDA(cudaMemsetAsync(iters, 0, sizeof(int32_t) * (size_t)B, st));
     return QPB_OK;

@@ -155,7 +155,8 @@ __host__ __device__ inline size_t lin_smem_per_warp(int K, int d) {
 }
 
 __global__ void k_lin_project(int n, int K, int B, const double* __restrict__ LhT,
-                              const int32_t* __restrict__ counts, int physical, double* __restrict__ rho) {
+                              const int32_t* __restrict__ counts, const double* __restrict__ h_in, int physical,
+                              double* __restrict__ rho) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int d = 1 << n, dd = d * d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -167,18 +168,22 @@ __global__ void k_lin_project(int n, int K, int B, const double* __restrict__ Lh
     jrot* rot = reinterpret_cast<jrot*>(h + dd);
 
     for (long b = (long)blockIdx.x * nw + warp; b < B; b += (long)gridDim.x * nw) {
-        const int32_t* c = counts + b * K;
-        long long tot = 0;
-        for (int k = lane; k < K; k += 32) tot += c[k];
+        if (h_in) {  // inversion already done by the DMMA GEMM (gemm_dmma.cu)
+            for (int idx = lane; idx < dd; idx += 32) h[idx] = h_in[b * dd + idx];
+        } else {
+            const int32_t* c = counts + b * K;
+            long long tot = 0;
+            for (int k = lane; k < K; k += 32) tot += c[k];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        const double total = (double)tot;
-        for (int k = lane; k < K; k += 32) f[k] = (double)c[k] / total;  // state.py:193
-        __syncwarp();
-        for (int idx = lane; idx < dd; idx += 32) {
-            double acc = 0.0;
-            for (int k = 0; k < K; ++k) acc += LhT[(long)k * dd + idx] * f[k];
-            h[idx] = acc;
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            const double total = (double)tot;
+            for (int k = lane; k < K; k += 32) f[k] = (double)c[k] / total;  // state.py:193
+            __syncwarp();
+            for (int idx = lane; idx < dd; idx += 32) {
+                double acc = 0.0;
+                for (int k = 0; k < K; ++k) acc += LhT[(long)k * dd + idx] * f[k];
+                h[idx] = acc;
+            }
         }
         __syncwarp();
         for (int e = lane; e < dd; e += 32) A[e] = herm_get(h, d, e / d, e % d);
@@ -435,7 +440,16 @@ int launch_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts,
     int rc = enable_smem(k_lin_project, smem);
     if (rc != QPB_OK) return rc;
     const int grid = grid_for_warps(B, warps, 4);
-    k_lin_project<<<grid, warps * 32, smem, st>>>(plan->n, plan->K, B, plan->LhT, counts, physical, rho);
+    const double* h_in = nullptr;
+    if (plan->n >= 3 && !getenv("QPB_NO_DMMA_GEMM")) {
+        // batched inversion on the FP64 tensor cores: H [B][D] = freq [B][K] * LhT [K][D]
+        double* H = static_cast<double*>(scratch(st, 3, sizeof(double) * (size_t)B * plan->D));
+        if (!H) return QPB_ERR_NOMEM;
+        rc = launch_gemm_counts(B, plan->D, plan->K, plan->K, counts, plan->LhT, H, st);
+        if (rc != QPB_OK) return rc;
+        h_in = H;
+    }
+    k_lin_project<<<grid, warps * 32, smem, st>>>(plan->n, plan->K, B, plan->LhT, counts, h_in, physical, rho);
     QPB_LAUNCHED("k_lin_project");
     return QPB_OK;
 }
