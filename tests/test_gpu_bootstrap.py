@@ -214,3 +214,100 @@ def test_process_bootstrap(qp, golden):
     probs = np.array([ostate.probabilities(g["dep1_povm"], __import__("oracle").pauli.matrix_to_bloch(o))
                       for o in g["dep1_outputs"]])
     assert np.abs(counts.mean(0) / 10000 - probs).max() < 5e-3
+
+
+# ----------------------------------------------------------------------------- BASELINE configs at full size
+
+def _plan_for(qp, n, povm, seed):
+    from quantpy_b200 import engine
+
+    rho = haar(n, seed)
+    pm = qp.generate_measurement_matrix(povm, n)
+    plan = engine.state_plan(pm, np.ones(pm.shape[0]) * 10000)
+    return rho, pm, plan, plan.probabilities(qp.Qobj(rho).bloch)[0]
+
+
+def test_config1_one_qubit_bootstrap_full_size(qp):
+    """BASELINE configs[0]: 1 qubit, 'proj-set', 10k shots, MLE estimate + 1000-sample bootstrap CI."""
+    rho = haar(1, 11)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(0)
+    tmg.experiment(10000)
+    est = tmg.point_estimate("mle")
+    assert qp.hs_dst(est, qp.Qobj(rho)) < 0.02
+    itv = qp.BootstrapStateInterval(tmg, n_points=1000, method="mle")
+    dist, cl = itv()
+    assert dist.shape == cl.shape == (1000,) and np.all(np.diff(dist) >= 0)
+    assert itv.state is tmg.reconstructed_state  # centre = the reconstructed state, interval.py:587
+    # the true state lies within the 99.9 % radius around the estimate
+    assert qp.hs_dst(est, qp.Qobj(rho)) < itv.cl_to_dist(0.999) * 1.5
+    assert 0.002 < itv.cl_to_dist(0.5) < 0.02
+
+
+def test_config3_three_qubit_lin_full_size(qp):
+    """BASELINE configs[2]: 3 qubits, 'lin' + projection (Jacobi), 1e5 resamples: physicality, idempotence,
+    and agreement with the oracle on a strided subset."""
+    from quantpy_b200 import _native as nt
+
+    rho, pm, plan, probs = _plan_for(qp, 3, "proj", 3)
+    B = 100000
+    out = plan.bootstrap(probs, B, 5, 0, rho, method="lin", dst="hs", keep=True)
+    est = nt.complex_to_host(out["rho"])
+    counts = out["counts"].cpu().numpy()
+    assert np.array_equal(counts.sum((1, 2)), np.full(B, 10000))
+    assert np.abs(np.trace(est, axis1=1, axis2=2) - 1).max() < 1e-12
+    assert np.abs(est - est.conj().transpose(0, 2, 1)).max() < 1e-15
+    assert np.linalg.eigvalsh(est).min() >= 0.5e-15  # clipped at 1e-15, then renormalised
+    idx = np.arange(0, B, 1009)
+    want = ostate.lin_estimate(counts[idx], pm, np.ones(1) * 10000)
+    assert fro(est[idx], want).max() < 1e-10
+    assert np.abs(out["dist"].cpu().numpy()[idx] - odist.hs(want, rho)).max() < 1e-10
+    # projecting an already physical state changes nothing (idempotence of _make_feasible)
+    again = ostate.make_feasible(est[idx])
+    assert fro(again, est[idx]).max() < 1e-12
+
+
+def test_config4_four_qubit_mle_full_size(qp):
+    """BASELINE configs[3]: 4 qubits (d = 16, 1296 outcomes), MLE, 1e4 resamples."""
+    from quantpy_b200 import _native as nt
+
+    rho, pm, plan, probs = _plan_for(qp, 4, "proj", 4)
+    B = 10000
+    out = plan.bootstrap(probs, B, 6, 0, rho, method="mle", max_iter=20, tol=1e-6, dst="hs", keep=True)
+    est = nt.complex_to_host(out["rho"])
+    counts = out["counts"].cpu().numpy()
+    assert np.array_equal(counts.sum((1, 2)), np.full(B, 10000))
+    assert np.abs(np.trace(est, axis1=1, axis2=2) - 1).max() < 1e-12
+    assert np.linalg.eigvalsh(est).min() > -1e-13
+    idx = np.array([0, 4999, 9999])
+    want, wits = ostate.mle_rrr(counts[idx], pm, np.ones(1) * 10000, max_iter=20, tol=1e-6, return_iters=True)
+    assert np.array_equal(out["iters"].cpu().numpy()[idx], wits)
+    assert fro(est[idx], want).max() < 1e-10
+    for i, j in enumerate(idx):  # likelihood never decreases from the linear-inversion start
+        start = ostate.lin_estimate(counts[j], pm, np.ones(1) * 10000)
+        assert ostate.neg_log_likelihood(est[j], counts[j], pm, np.ones(1) * 10000) <= \
+            ostate.neg_log_likelihood(start, counts[j], pm, np.ones(1) * 10000) + 1e-12
+
+
+@pytest.mark.parametrize("n,B", [(1, 20000), (2, 600)])
+def test_config5_process_bootstrap_full_size(qp, n, B):
+    """BASELINE configs[4]: depolarising channel, lifp + CPTP projection: every bootstrap estimate is CPTP,
+    and a strided subset matches the oracle."""
+    chan = qp.channel.depolarizing(0.1, n)
+    tmg = qp.ProcessTomograph(chan, "sic")
+    np.random.seed(0)
+    tmg.experiment(10000, "proj-set")
+    counts = tmg.sample_counts(B, 10000, "proj-set", seed=9)
+    choi, iters = tmg.point_estimate_batch(counts, cptp=True, return_iters=True)
+    d = 2**n
+    rho_in = np.einsum("niaja->nij", choi.reshape(B, d, d, d, d))
+    assert np.abs(rho_in - np.eye(d)).max() < 1e-5       # trace preserving (Channel.is_cptp's tolerance)
+    assert np.linalg.eigvalsh(0.5 * (choi + choi.conj().transpose(0, 2, 1))).min() > -1e-5  # completely positive
+    idx = np.arange(0, B, max(1, B // 7))
+    inputs = oproc.input_states("sic", n)
+    pm = qp.generate_measurement_matrix("proj-set", n)
+    want, wit = oproc.lifp_estimate(counts[idx], inputs, pm, np.ones(pm.shape[0]) * 10000, cptp=True, return_iters=True)
+    assert fro(choi[idx], want).max() < 1e-9 and np.abs(iters[idx] - wit).max() <= 1
+    itv = qp.BootstrapProcessInterval(tmg, n_points=B // 2, channel=chan)
+    itv.setup(seed=3)
+    assert np.all(np.diff(itv.dist) >= 0) and itv.dist[0] > 0
