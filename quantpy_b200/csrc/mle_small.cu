@@ -219,14 +219,14 @@ struct ConstTables {
     double tab2[K * (1 << (2 * N))];
 };
 
-// 1/y to within an ulp: hardware seed (2^-23) + two Newton steps, all on the FP64 pipe.
+// 1/y to within an ulp: hardware seed x0 (relative error e <= 2^-23) and one third-order correction
+// x0 (1 + e + e^2), truncation e^3 <= 2^-69 -- three FMAs on the FP64 pipe.
 __device__ __forceinline__ double fast_rcp(double y) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(y));
-    double e = fma(-y, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-y, x, 1.0);
-    return fma(x, e, x);
+    const double e = fma(-y, x, 1.0);
+    const double t = fma(e, e, e);
+    return fma(x, t, x);
 }
 
 template <int N, int K>
@@ -476,10 +476,10 @@ struct PauliParams {
     double epsp[36];      // 1e-10 / c_k per slot (1.0 for unused slots)
     int slot_of_col[36];  // canonical slot of count column k
     int K;
+    int uniform;          // all used slots have the same guard (then every entry of epsp holds it)
 };
 
-__device__ int g_lane_limit = 32;  // experiment: lanes >= this never take samples
-
+template <bool UNIFORM_GUARD>  // all used slots share one 1e-10/c: fold it into S_00 instead of 36 additions
 __global__ void __launch_bounds__(kSmallThreads)
 k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* __restrict__ counts,
                  const double* __restrict__ rho0, int max_iter, double tol, double* __restrict__ rho,
@@ -494,7 +494,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
     double h[D];
     int it = 0;
     long b = -1;
-    bool alive = lane < g_lane_limit;
+    bool alive = true;
     const double tol2 = tol * tol;
 
     while (true) {
@@ -550,6 +550,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
             } else {
                 double S[16], g[16];
                 pauli2::all_s(h, S);
+                if (UNIFORM_GUARD) S[0] += pp.epsp[0];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) g[e] = 0.0;
 #pragma unroll
@@ -564,7 +565,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
                     for (int be = 0; be < 6; ++be) {
                         const int bq = be / 2 + 1;
                         const double q = (be & 1) ? t[0] - t[bq] : t[0] + t[bq];
-                        w[be] = q + pp.epsp[al * 6 + be];
+                        w[be] = UNIFORM_GUARD ? q : q + pp.epsp[al * 6 + be];
                     }
 #pragma unroll
                     for (int be = 0; be < 6; ++be) w[be] = fs[(al * 6 + be) * kSmallThreads + tid] * fast_rcp(w[be]);
@@ -652,6 +653,12 @@ static bool detect_pauli2(const double* A, int K, PauliParams* pp) {
         pp->slot_of_col[k] = slot;
         pp->epsp[slot] = kLogGuard / c;
     }
+    const double first = pp->epsp[pp->slot_of_col[0]];
+    pp->uniform = 1;
+    for (int k = 0; k < K; ++k)
+        if (pp->epsp[pp->slot_of_col[k]] != first) pp->uniform = 0;
+    if (pp->uniform)
+        for (int sl = 0; sl < 36; ++sl) pp->epsp[sl] = first;  // unused slots have f = 0, any positive guard works
     return true;
 }
 
@@ -683,18 +690,14 @@ int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, c
         if (detect_pauli2(plan->A_host, plan->K, &pp)) {
             const size_t smem = sizeof(double) * 36 * kSmallThreads;
             int per_sm = 1;
-            QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mle_rrr_pauli2, kSmallThreads, smem));
+            auto pk = pp.uniform ? k_mle_rrr_pauli2<true> : k_mle_rrr_pauli2<false>;
+            QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, kSmallThreads, smem));
             if (per_sm < 1) per_sm = 1;
             if (per_sm > kMaxBlocksPerSm) per_sm = kMaxBlocksPerSm;
             long blocks = (long)num_sms() * per_sm;
             const long need = ((long)B + kSmallThreads - 1) / kSmallThreads;
             if (blocks > need) blocks = need;
-            if (const char* e = getenv("QPB_LANE_LIMIT")) {
-                const int v = atoi(e);
-                cudaMemcpyToSymbolAsync(g_lane_limit, &v, sizeof(int), 0, cudaMemcpyHostToDevice, st);
-            }
-            k_mle_rrr_pauli2<<<(int)blocks, kSmallThreads, smem, st>>>(pp, B, counts, rho0, max_iter, tol, rho, iters,
-                                                                      queue);
+            pk<<<(int)blocks, kSmallThreads, smem, st>>>(pp, B, counts, rho0, max_iter, tol, rho, iters, queue);
             QPB_LAUNCHED("k_mle_rrr_pauli2");
             return QPB_OK;
         }
