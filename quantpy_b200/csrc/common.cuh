@@ -86,6 +86,23 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
+// 1/sqrt(y) and 1/y to ~1 ulp from the hardware seeds (2^-22 / 2^-23) and Newton steps on the FP64 pipe;
+// a fraction of the instruction count of IEEE sqrt/div, which dominated the Jacobi rotation set-up.
+__device__ __forceinline__ double fast_rsqrt(double y) {
+    double x;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(y));
+    const double hy = 0.5 * y;
+    x = x * fma(-hy * x, x, 1.5);
+    x = x * fma(-hy * x, x, 1.5);
+    return x;
+}
+__device__ __forceinline__ double fast_recip(double y) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(y));
+    const double e = fma(-y, x, 1.0);
+    return fma(x, fma(e, e, e), x);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  key = 64-bit seed, counter = 128 bits.
 // ---------------------------------------------------------------------------------------------

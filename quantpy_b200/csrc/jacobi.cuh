@@ -29,24 +29,32 @@ __device__ __forceinline__ void jacobi_pair(int d, int round, int i, int& p, int
     q = a < b ? b : a;
 }
 
-// A: d*d row-major complex Hermitian (destroyed: diagonal holds eigenvalues on return).
-// V: d*d row-major; on return column j is the eigenvector of eigenvalue A[j][j].  If !WANT_V, V unused.
+// Leading dimension of the shared-memory matrices: d + 1 complex (16 B) elements, so that the d rows of
+// one column fall into different banks (with ld = d the column updates were 8- to 16-way bank conflicted and
+// the kernel ran at 96 % of the shared-memory pipe, profiles/README_r1.md).
+__host__ __device__ inline int jacobi_ld(int d) { return d + 1; }
+
+// A: d x d complex Hermitian, row-major with leading dimension ld = jacobi_ld(d) (destroyed: the diagonal holds
+//    the eigenvalues on return).
+// V: same layout; on return column j is the eigenvector of eigenvalue A[j][j].  If !WANT_V, V is unused.
 // rot: d/2 jrot entries of scratch.  All pointers are shared memory private to this warp.
 template <bool WANT_V>
 __device__ void warp_jacobi(cplx* __restrict__ A, cplx* __restrict__ V, jrot* __restrict__ rot, int d, int lane) {
     const int dd = d * d;
     const int half = d >> 1;
+    const int ld = jacobi_ld(d);
     if (WANT_V) {
         for (int e = lane; e < dd; e += 32) {
-            V[e].re = (e / d == e % d) ? 1.0 : 0.0;
-            V[e].im = 0.0;
+            V[(e / d) * ld + e % d].re = (e / d == e % d) ? 1.0 : 0.0;
+            V[(e / d) * ld + e % d].im = 0.0;
         }
     }
     __syncwarp();
     for (int sweep = 0; sweep < 40; ++sweep) {
         double off = 0.0, fro = 0.0;
         for (int e = lane; e < dd; e += 32) {
-            double m2 = A[e].re * A[e].re + A[e].im * A[e].im;
+            const cplx z = A[(e / d) * ld + e % d];
+            double m2 = z.re * z.re + z.im * z.im;
             fro += m2;
             if (e / d != e % d) off += m2;
         }
@@ -58,8 +66,8 @@ __device__ void warp_jacobi(cplx* __restrict__ A, cplx* __restrict__ V, jrot* __
             if (lane < half) {
                 int p, q;
                 jacobi_pair(d, round, lane, p, q);
-                double al = A[p * d + p].re, ga = A[q * d + q].re;
-                double br = A[p * d + q].re, bi = A[p * d + q].im;
+                double al = A[p * ld + p].re, ga = A[q * ld + q].re;
+                double br = A[p * ld + q].re, bi = A[p * ld + q].im;
                 double b2 = br * br + bi * bi;
                 jrot r;
                 r.p = p;
@@ -67,13 +75,16 @@ __device__ void warp_jacobi(cplx* __restrict__ A, cplx* __restrict__ V, jrot* __
                 if (b2 <= tiny2) {
                     r.c = 1.0; r.s = 0.0; r.ur = 1.0; r.ui = 0.0;
                 } else {
-                    double ab = sqrt(b2);
-                    double tau = (ga - al) / (2.0 * ab);
-                    double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                    r.c = 1.0 / sqrt(1.0 + t * t);
+                    // same rotation as LAPACK-style Jacobi, with reciprocal square roots instead of sqrt + div
+                    const double iab = fast_rsqrt(b2);           // 1 / |beta|
+                    const double tau = 0.5 * (ga - al) * iab;
+                    const double x = fma(tau, tau, 1.0);
+                    const double root = x * fast_rsqrt(x);       // sqrt(1 + tau^2)
+                    const double t = (tau >= 0.0 ? 1.0 : -1.0) * fast_recip(fabs(tau) + root);
+                    r.c = fast_rsqrt(fma(t, t, 1.0));
                     r.s = t * r.c;
-                    r.ur = br / ab;
-                    r.ui = bi / ab;
+                    r.ur = br * iab;
+                    r.ui = bi * iab;
                 }
                 rot[lane] = r;
             }
@@ -82,7 +93,7 @@ __device__ void warp_jacobi(cplx* __restrict__ A, cplx* __restrict__ V, jrot* __
             for (int w = lane; w < half * d; w += 32) {
                 const jrot r = rot[w / d];
                 const int row = w % d;
-                cplx x = A[row * d + r.p], y = A[row * d + r.q];
+                cplx x = A[row * ld + r.p], y = A[row * ld + r.q];
                 // su = s*u ; A'_rp = c x - s conj(u) y ; A'_rq = s u x + c y
                 double sur = r.s * r.ur, sui = r.s * r.ui;
                 cplx nx, ny;
@@ -90,17 +101,17 @@ __device__ void warp_jacobi(cplx* __restrict__ A, cplx* __restrict__ V, jrot* __
                 nx.im = r.c * x.im - (sur * y.im - sui * y.re);
                 ny.re = (sur * x.re - sui * x.im) + r.c * y.re;
                 ny.im = (sur * x.im + sui * x.re) + r.c * y.im;
-                A[row * d + r.p] = nx;
-                A[row * d + r.q] = ny;
+                A[row * ld + r.p] = nx;
+                A[row * ld + r.q] = ny;
                 if (WANT_V) {
-                    cplx vx = V[row * d + r.p], vy = V[row * d + r.q];
+                    cplx vx = V[row * ld + r.p], vy = V[row * ld + r.q];
                     cplx mx, my;
                     mx.re = r.c * vx.re - (sur * vy.re + sui * vy.im);
                     mx.im = r.c * vx.im - (sur * vy.im - sui * vy.re);
                     my.re = (sur * vx.re - sui * vx.im) + r.c * vy.re;
                     my.im = (sur * vx.im + sui * vx.re) + r.c * vy.im;
-                    V[row * d + r.p] = mx;
-                    V[row * d + r.q] = my;
+                    V[row * ld + r.p] = mx;
+                    V[row * ld + r.q] = my;
                 }
             }
             __syncwarp();
@@ -108,25 +119,25 @@ __device__ void warp_jacobi(cplx* __restrict__ A, cplx* __restrict__ V, jrot* __
             for (int w = lane; w < half * d; w += 32) {
                 const jrot r = rot[w / d];
                 const int col = w % d;
-                cplx x = A[r.p * d + col], y = A[r.q * d + col];
+                cplx x = A[r.p * ld + col], y = A[r.q * ld + col];
                 double sur = r.s * r.ur, sui = r.s * r.ui;
                 cplx nx, ny;
                 nx.re = r.c * x.re - (sur * y.re - sui * y.im);
                 nx.im = r.c * x.im - (sur * y.im + sui * y.re);
                 ny.re = (sur * x.re + sui * x.im) + r.c * y.re;
                 ny.im = (sur * x.im - sui * x.re) + r.c * y.im;
-                A[r.p * d + col] = nx;
-                A[r.q * d + col] = ny;
+                A[r.p * ld + col] = nx;
+                A[r.q * ld + col] = ny;
             }
             __syncwarp();
             if (lane < half) {
                 const jrot r = rot[lane];
                 if (r.s != 0.0) {
-                    A[r.p * d + r.q].re = 0.0; A[r.p * d + r.q].im = 0.0;
-                    A[r.q * d + r.p].re = 0.0; A[r.q * d + r.p].im = 0.0;
+                    A[r.p * ld + r.q].re = 0.0; A[r.p * ld + r.q].im = 0.0;
+                    A[r.q * ld + r.p].re = 0.0; A[r.q * ld + r.p].im = 0.0;
                 }
-                A[r.p * d + r.p].im = 0.0;
-                A[r.q * d + r.q].im = 0.0;
+                A[r.p * ld + r.p].im = 0.0;
+                A[r.q * ld + r.q].im = 0.0;
             }
             __syncwarp();
         }

@@ -22,12 +22,13 @@ __device__ __forceinline__ void jacobi_rotate(RegMat<d>& A, RegMat<d>& V, double
     const double br = A.re[P][Q], bi = A.im[P][Q];
     const double b2 = br * br + bi * bi;
     if (b2 <= tiny2) return;
-    const double ab = sqrt(b2);
-    const double tau = (A.re[Q][Q] - A.re[P][P]) / (2.0 * ab);
-    const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-    const double c = 1.0 / sqrt(1.0 + t * t);
+    const double iab = fast_rsqrt(b2);
+    const double tau = 0.5 * (A.re[Q][Q] - A.re[P][P]) * iab;
+    const double x = fma(tau, tau, 1.0);
+    const double t = (tau >= 0.0 ? 1.0 : -1.0) * fast_recip(fabs(tau) + x * fast_rsqrt(x));
+    const double c = fast_rsqrt(fma(t, t, 1.0));
     const double s = t * c;
-    const double sur = s * br / ab, sui = s * bi / ab;  // s * u, u = A_pq / |A_pq|
+    const double sur = s * br * iab, sui = s * bi * iab;  // s * u, u = A_pq / |A_pq|
 #pragma unroll
     for (int r = 0; r < d; ++r) {  // columns: X'_rp = c X_rp - s conj(u) X_rq ; X'_rq = s u X_rp + c X_rq
         {

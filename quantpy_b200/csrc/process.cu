@@ -56,7 +56,8 @@ __global__ void k_lifp(int S, int K, int ss, int B, const double* __restrict__ L
 }
 
 __host__ __device__ inline size_t cptp_smem_per_warp(int s) {
-    return sizeof(cplx) * 7 * (size_t)s * s + sizeof(jrot) * (size_t)(s / 2 + 1) + sizeof(cplx) * 16;
+    return sizeof(cplx) * (5 * (size_t)s * s + 2 * (size_t)s * jacobi_ld(s)) + sizeof(jrot) * (size_t)(s / 2 + 1) +
+           sizeof(cplx) * 16;
 }
 
 // Alternating projection of process.py:237-257, one warp per Choi matrix.
@@ -70,10 +71,11 @@ __global__ void k_cptp(int d, int B, const double* __restrict__ choi_in, int n_i
     cplx* p = x + ss;
     cplx* q = p + ss;
     cplx* y = q + ss;
-    cplx* A = y + ss;
-    cplx* V = A + ss;
-    cplx* T = V + ss;
-    cplx* rin = T + ss;  // d*d <= 16
+    cplx* T = y + ss;
+    const int ld = jacobi_ld(s);
+    cplx* A = T + ss;        // A, V: padded leading dimension for the Jacobi solve
+    cplx* V = A + s * ld;
+    cplx* rin = V + s * ld;  // d*d <= 16
     jrot* rot = reinterpret_cast<jrot*>(rin + 16);
     const double invd = 1.0 / d;
 
@@ -127,8 +129,8 @@ __global__ void k_cptp(int d, int B, const double* __restrict__ choi_in, int n_i
             // ---- x' = CP(y' + q): eigh, clip at 1e-12, recompose
             for (int e = lane; e < ss; e += 32) {
                 const int r = e / s, c = e % s, et = c * s + r;
-                A[e].re = 0.5 * ((y[e].re + q[e].re) + (y[et].re + q[et].re));
-                A[e].im = 0.5 * ((y[e].im + q[e].im) - (y[et].im + q[et].im));
+                A[r * ld + c].re = 0.5 * ((y[e].re + q[e].re) + (y[et].re + q[et].re));
+                A[r * ld + c].im = 0.5 * ((y[e].im + q[e].im) - (y[et].im + q[et].im));
             }
             __syncwarp();
             warp_jacobi<true>(A, V, rot, s, lane);
@@ -137,8 +139,8 @@ __global__ void k_cptp(int d, int B, const double* __restrict__ choi_in, int n_i
                 const int r = e / s, c = e % s;
                 double re = 0.0, im = 0.0;
                 for (int j = 0; j < s; ++j) {
-                    const double lam = fmax(A[j * s + j].re, kClipChoi);
-                    const cplx u = V[r * s + j], v = V[c * s + j];
+                    const double lam = fmax(A[j * ld + j].re, kClipChoi);
+                    const cplx u = V[r * ld + j], v = V[c * ld + j];
                     re += lam * (u.re * v.re + u.im * v.im);
                     im += lam * (u.im * v.re - u.re * v.im);
                 }

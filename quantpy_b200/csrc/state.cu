@@ -111,18 +111,20 @@ __global__ void k_povm_probs(int K, int D, int B, const double* __restrict__ M, 
 // ------------------------------------------------------------------------------------------------
 // helpers on shared-memory d x d complex matrices owned by one warp
 // ------------------------------------------------------------------------------------------------
+// all matrices below use the padded leading dimension ld = jacobi_ld(d)
 __device__ __forceinline__ void warp_matmul(cplx* __restrict__ C, const cplx* __restrict__ X,
                                             const cplx* __restrict__ Y, int d, int lane) {
+    const int ld = jacobi_ld(d);
     for (int e = lane; e < d * d; e += 32) {
         const int a = e / d, b = e % d;
         double re = 0.0, im = 0.0;
         for (int c = 0; c < d; ++c) {
-            const cplx x = X[a * d + c], y = Y[c * d + b];
+            const cplx x = X[a * ld + c], y = Y[c * ld + b];
             re += x.re * y.re - x.im * y.im;
             im += x.re * y.im + x.im * y.re;
         }
-        C[e].re = re;
-        C[e].im = im;
+        C[a * ld + b].re = re;
+        C[a * ld + b].im = im;
     }
 }
 
@@ -130,18 +132,19 @@ __device__ __forceinline__ void warp_matmul(cplx* __restrict__ C, const cplx* __
 // mode 0: max(lambda, floor) ; mode 1: sqrt(max(lambda, 0))
 __device__ __forceinline__ void warp_recompose(cplx* __restrict__ C, const cplx* __restrict__ A,
                                                const cplx* __restrict__ V, int d, int lane, int mode, double floor_) {
+    const int ld = jacobi_ld(d);
     for (int e = lane; e < d * d; e += 32) {
         const int a = e / d, b = e % d;
         double re = 0.0, im = 0.0;
         for (int j = 0; j < d; ++j) {
-            double lam = A[j * d + j].re;
+            double lam = A[j * ld + j].re;
             lam = (mode == 0) ? fmax(lam, floor_) : sqrt(fmax(lam, 0.0));
-            const cplx x = V[a * d + j], y = V[b * d + j];  // x * conj(y)
+            const cplx x = V[a * ld + j], y = V[b * ld + j];  // x * conj(y)
             re += lam * (x.re * y.re + x.im * y.im);
             im += lam * (x.im * y.re - x.re * y.im);
         }
-        C[e].re = re;
-        C[e].im = im;
+        C[a * ld + b].re = re;
+        C[a * ld + b].im = im;
     }
 }
 
@@ -150,8 +153,8 @@ __device__ __forceinline__ void warp_recompose(cplx* __restrict__ C, const cplx*
 // One warp per sample.  shared per warp: f[K] | h[D] | A[dd] | V[dd] | rot[d/2]
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t lin_smem_per_warp(int K, int d) {
-    const int dd = d * d;
-    return sizeof(double) * (size_t)(K + dd) + sizeof(cplx) * 2 * (size_t)dd + sizeof(jrot) * (size_t)(d / 2 + 1);
+    const int dd = d * d, pad = d * jacobi_ld(d);
+    return sizeof(double) * (size_t)(K + dd) + sizeof(cplx) * 2 * (size_t)pad + sizeof(jrot) * (size_t)(d / 2 + 1);
 }
 
 __global__ void k_lin_project(int n, int K, int B, const double* __restrict__ LhT,
@@ -160,10 +163,11 @@ __global__ void k_lin_project(int n, int K, int B, const double* __restrict__ Lh
     extern __shared__ __align__(16) unsigned char smraw[];
     const int d = 1 << n, dd = d * d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int ld = jacobi_ld(d);
     unsigned char* base = smraw + (size_t)warp * lin_smem_per_warp(K, d);
     cplx* A = reinterpret_cast<cplx*>(base);
-    cplx* V = A + dd;
-    double* f = reinterpret_cast<double*>(V + dd);
+    cplx* V = A + d * ld;
+    double* f = reinterpret_cast<double*>(V + d * ld);
     double* h = f + K;
     jrot* rot = reinterpret_cast<jrot*>(h + dd);
 
@@ -186,25 +190,25 @@ __global__ void k_lin_project(int n, int K, int B, const double* __restrict__ Lh
             }
         }
         __syncwarp();
-        for (int e = lane; e < dd; e += 32) A[e] = herm_get(h, d, e / d, e % d);
+        for (int e = lane; e < dd; e += 32) A[(e / d) * ld + e % d] = herm_get(h, d, e / d, e % d);
         __syncwarp();
         double* out = rho + b * 2 * dd;
         if (!physical) {
             for (int e = lane; e < dd; e += 32) {
-                out[2 * e] = A[e].re;
-                out[2 * e + 1] = A[e].im;
+                out[2 * e] = A[(e / d) * ld + e % d].re;
+                out[2 * e + 1] = A[(e / d) * ld + e % d].im;
             }
         } else {
             warp_jacobi<true>(A, V, rot, d, lane);
             double tr = 0.0;
-            for (int j = 0; j < d; ++j) tr += fmax(A[j * d + j].re, kClipState);
+            for (int j = 0; j < d; ++j) tr += fmax(A[j * ld + j].re, kClipState);
             const double inv = 1.0 / tr;
             for (int e = lane; e < dd; e += 32) {
                 const int a = e / d, bb = e % d;
                 double re = 0.0, im = 0.0;
                 for (int j = 0; j < d; ++j) {
-                    const double lam = fmax(A[j * d + j].re, kClipState);
-                    const cplx x = V[a * d + j], y = V[bb * d + j];
+                    const double lam = fmax(A[j * ld + j].re, kClipState);
+                    const cplx x = V[a * ld + j], y = V[bb * ld + j];
                     re += lam * (x.re * y.re + x.im * y.im);
                     im += lam * (x.im * y.re - x.re * y.im);
                 }
@@ -336,7 +340,7 @@ __global__ void k_mle_rrr_generic(int n, int K, int B, const double* __restrict_
 // k8: distances (geometry.py:5-56).  One warp per sample; shared per warp: 4 dd cplx + rot
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t dist_smem_per_warp(int d) {
-    return sizeof(cplx) * 4 * (size_t)d * d + sizeof(jrot) * (size_t)(d / 2 + 1);
+    return sizeof(cplx) * 4 * (size_t)d * jacobi_ld(d) + sizeof(jrot) * (size_t)(d / 2 + 1);
 }
 
 __global__ void k_distance(int d, int B, const double* __restrict__ rho, const double* __restrict__ ref, int kind,
@@ -344,12 +348,13 @@ __global__ void k_distance(int d, int B, const double* __restrict__ rho, const d
     extern __shared__ __align__(16) unsigned char smraw[];
     const int dd = d * d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const int ld = jacobi_ld(d), pad = d * ld;
     unsigned char* base = smraw + (size_t)warp * dist_smem_per_warp(d);
     cplx* A = reinterpret_cast<cplx*>(base);
-    cplx* V = A + dd;
-    cplx* T1 = V + dd;
-    cplx* T2 = T1 + dd;
-    jrot* rot = reinterpret_cast<jrot*>(T2 + dd);
+    cplx* V = A + pad;
+    cplx* T1 = V + pad;
+    cplx* T2 = T1 + pad;
+    jrot* rot = reinterpret_cast<jrot*>(T2 + pad);
     const cplx* refc = reinterpret_cast<const cplx*>(ref);
 
     for (long b = (long)blockIdx.x * nw + warp; b < B; b += (long)gridDim.x * nw) {
@@ -372,22 +377,22 @@ __global__ void k_distance(int d, int B, const double* __restrict__ rho, const d
             for (int e = lane; e < dd; e += 32) {
                 const int a = e / d, bb = e % d;
                 const cplx p = x[e], q = refc[e], pt = x[bb * d + a], qt = refc[bb * d + a];
-                A[e].re = 0.5 * ((p.re - q.re) + (pt.re - qt.re));
-                A[e].im = 0.5 * ((p.im - q.im) - (pt.im - qt.im));
+                A[a * ld + bb].re = 0.5 * ((p.re - q.re) + (pt.re - qt.re));
+                A[a * ld + bb].im = 0.5 * ((p.im - q.im) - (pt.im - qt.im));
             }
             __syncwarp();
             warp_jacobi<false>(A, V, rot, d, lane);
             double s = 0.0;
-            for (int j = 0; j < d; ++j) s += fabs(A[j * d + j].re);
+            for (int j = 0; j < d; ++j) s += fabs(A[j * ld + j].re);
             val = 0.5 * s;
         } else {
             // 1 - (Tr sqrt( sqrt(x) ref sqrt(x) ))^2  (geometry.py:52), eigenvalue form
             for (int e = lane; e < dd; e += 32) {
                 const int a = e / d, bb = e % d;
                 const cplx p = x[e], pt = x[bb * d + a];
-                A[e].re = 0.5 * (p.re + pt.re);
-                A[e].im = 0.5 * (p.im - pt.im);
-                T2[e] = refc[e];
+                A[a * ld + bb].re = 0.5 * (p.re + pt.re);
+                A[a * ld + bb].im = 0.5 * (p.im - pt.im);
+                T2[a * ld + bb] = refc[e];
             }
             __syncwarp();
             warp_jacobi<true>(A, V, rot, d, lane);
@@ -399,14 +404,14 @@ __global__ void k_distance(int d, int B, const double* __restrict__ rho, const d
             __syncwarp();
             for (int e = lane; e < dd; e += 32) {
                 const int a = e / d, bb = e % d;
-                const cplx p = V[e], pt = V[bb * d + a];
-                A[e].re = 0.5 * (p.re + pt.re);
-                A[e].im = 0.5 * (p.im - pt.im);
+                const cplx p = V[a * ld + bb], pt = V[bb * ld + a];
+                A[a * ld + bb].re = 0.5 * (p.re + pt.re);
+                A[a * ld + bb].im = 0.5 * (p.im - pt.im);
             }
             __syncwarp();
             warp_jacobi<false>(A, T1, rot, d, lane);
             double s = 0.0;
-            for (int j = 0; j < d; ++j) s += sqrt(fmax(A[j * d + j].re, 0.0));
+            for (int j = 0; j < d; ++j) s += sqrt(fmax(A[j * ld + j].re, 0.0));
             val = 1.0 - s * s;
         }
         if (lane == 0) dist[b] = (val < kZeroBelow) ? 0.0 : val;
