@@ -25,9 +25,32 @@ struct Axis {
     static constexpr int d = 1 << N;
     static constexpr int D = d * d;          // 4^N
     static constexpr int K6 = ipow(6, N);    // canonical slots
-    // doubles of shared memory per warp: rho, R, W (complex d x d each) + two contraction buffers + f
-    static constexpr int per_warp = 3 * 2 * D + 3 * K6;
+    static constexpr int ld = d + 1;         // padded leading dimension of the complex matrices (bank conflicts)
+    // doubles of shared memory per warp: rho, R, W (complex d x ld each) + two contraction buffers + f
+    static constexpr int per_warp = 3 * 2 * d * ld + 3 * K6;
 };
+
+// One sample is processed by a group of GS threads: a warp (GS = 32) or a whole CTA (GS = blockDim.x).
+template <int GS>
+__device__ __forceinline__ void gsync() {
+    if constexpr (GS == 32) __syncwarp();
+    else __syncthreads();
+}
+template <int GS>
+__device__ __forceinline__ double gsum(double v, double* red, int tid) {
+    v = warp_sum(v);
+    if constexpr (GS == 32) {
+        return v;
+    } else {
+        __syncthreads();  // red may still be read from the previous reduction
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < GS / 32; ++w) s += red[w];
+        return s;
+    }
+}
 
 // index of matrix element (a, b) in the digit-interleaved order: digit_q = 2 a_q + b_q, first qubit most significant
 template <int N>
@@ -42,13 +65,13 @@ __device__ __forceinline__ int interleave(int a, int b) {
 }
 
 // forward fast Pauli transform, in place on W (complex, digit-interleaved): W[i] <- Tr(sigma_i M)
-template <int N>
+template <int N, int GS>
 __device__ __forceinline__ void pauli_forward(double2* __restrict__ W, int lane) {
     constexpr int D = Axis<N>::D;
 #pragma unroll
     for (int q = 0; q < N; ++q) {
         const int stride = 1 << (2 * (N - 1 - q));
-        for (int g = lane; g < D / 4; g += 32) {
+        for (int g = lane; g < D / 4; g += GS) {
             const int idx = (g / stride) * 4 * stride + (g % stride);
             const double2 v0 = W[idx], v1 = W[idx + stride], v2 = W[idx + 2 * stride], v3 = W[idx + 3 * stride];
             W[idx] = make_double2(v0.x + v3.x, v0.y + v3.y);                   // I
@@ -56,18 +79,18 @@ __device__ __forceinline__ void pauli_forward(double2* __restrict__ W, int lane)
             W[idx + 2 * stride] = make_double2(-(v1.y - v2.y), v1.x - v2.x);   // Y = i (v1 - v2)
             W[idx + 3 * stride] = make_double2(v0.x - v3.x, v0.y - v3.y);      // Z
         }
-        __syncwarp();
+        gsync<GS>();
     }
 }
 
 // inverse: W[i] = g_i (complex) -> W[e(a,b)] = (sum_i g_i sigma_i)[a][b]
-template <int N>
+template <int N, int GS>
 __device__ __forceinline__ void pauli_inverse(double2* __restrict__ W, int lane) {
     constexpr int D = Axis<N>::D;
 #pragma unroll
     for (int q = 0; q < N; ++q) {
         const int stride = 1 << (2 * (N - 1 - q));
-        for (int g = lane; g < D / 4; g += 32) {
+        for (int g = lane; g < D / 4; g += GS) {
             const int idx = (g / stride) * 4 * stride + (g % stride);
             const double2 gi = W[idx], gx = W[idx + stride], gy = W[idx + 2 * stride], gz = W[idx + 3 * stride];
             W[idx] = make_double2(gi.x + gz.x, gi.y + gz.y);                   // (0,0)
@@ -75,27 +98,27 @@ __device__ __forceinline__ void pauli_inverse(double2* __restrict__ W, int lane)
             W[idx + 2 * stride] = make_double2(gx.x - gy.y, gx.y + gy.x);      // (1,0) = gx + i gy
             W[idx + 3 * stride] = make_double2(gi.x - gz.x, gi.y - gz.y);      // (1,1)
         }
-        __syncwarp();
+        gsync<GS>();
     }
 }
 
 // stage Q of the axis map: in [6^Q][4][4^(N-1-Q)] -> out [6^Q][6][4^(N-1-Q)]
-template <int N, int Q>
+template <int N, int Q, int GS>
 __device__ __forceinline__ void axis_forward(const double* __restrict__ in, double* __restrict__ out, int lane) {
     constexpr int P4 = ipow(4, N - 1 - Q), PRE = ipow(6, Q);
-    for (int o = lane; o < PRE * 6 * P4; o += 32) {
+    for (int o = lane; o < PRE * 6 * P4; o += GS) {
         const int post = o % P4, al = (o / P4) % 6, pre = o / (6 * P4);
         const double x0 = in[(pre * 4) * P4 + post], xa = in[(pre * 4 + (al >> 1) + 1) * P4 + post];
         out[o] = (al & 1) ? x0 - xa : x0 + xa;
     }
-    __syncwarp();
+    gsync<GS>();
 }
 
 // adjoint of stage Q: in [6^Q][6][4^(N-1-Q)] -> out [6^Q][4][4^(N-1-Q)]
-template <int N, int Q>
+template <int N, int Q, int GS>
 __device__ __forceinline__ void axis_adjoint(const double* __restrict__ in, double* __restrict__ out, int lane) {
     constexpr int P4 = ipow(4, N - 1 - Q), PRE = ipow(6, Q);
-    for (int o = lane; o < PRE * 4 * P4; o += 32) {
+    for (int o = lane; o < PRE * 4 * P4; o += GS) {
         const int post = o % P4, dig = (o / P4) % 4, pre = o / (4 * P4);
         const double* src = in + (pre * 6) * P4 + post;
         double v;
@@ -103,45 +126,45 @@ __device__ __forceinline__ void axis_adjoint(const double* __restrict__ in, doub
         else v = src[(2 * (dig - 1)) * P4] - src[(2 * (dig - 1) + 1) * P4];
         out[o] = v;
     }
-    __syncwarp();
+    gsync<GS>();
 }
 
-template <int N, int Q = 0>
+template <int N, int GS, int Q = 0>
 __device__ __forceinline__ double* axis_forward_all(double* a, double* b, int lane) {
     if constexpr (Q == N) {
         return a;  // result lives in `a`
     } else {
-        axis_forward<N, Q>(a, b, lane);
-        return axis_forward_all<N, Q + 1>(b, a, lane);
+        axis_forward<N, Q, GS>(a, b, lane);
+        return axis_forward_all<N, GS, Q + 1>(b, a, lane);
     }
 }
-template <int N, int Q = N - 1>
+template <int N, int GS, int Q = N - 1>
 __device__ __forceinline__ double* axis_adjoint_all(double* a, double* b, int lane) {
     if constexpr (Q < 0) {
         return a;
     } else {
-        axis_adjoint<N, Q>(a, b, lane);
-        return axis_adjoint_all<N, Q - 1>(b, a, lane);
+        axis_adjoint<N, Q, GS>(a, b, lane);
+        return axis_adjoint_all<N, GS, Q - 1>(b, a, lane);
     }
 }
 
 // C = X * Y for d x d complex matrices in shared memory (row-major); each lane owns whole output elements
-template <int N>
+template <int N, int GS>
 __device__ __forceinline__ void cmatmul(double2* __restrict__ C, const double2* __restrict__ X,
                                         const double2* __restrict__ Y, int lane) {
-    constexpr int d = Axis<N>::d, D = Axis<N>::D;
+    constexpr int d = Axis<N>::d, D = Axis<N>::D, ld = Axis<N>::ld;
     constexpr int TJ = (D / 32 >= 4) ? 4 : (D / 32 >= 2 ? 2 : 1);  // outputs per lane per pass (same row)
-    for (int t = lane; t < D / TJ; t += 32) {
+    for (int t = lane; t < D / TJ; t += GS) {
         const int a = t / (d / TJ), b0 = (t % (d / TJ)) * TJ;
         double re[TJ], im[TJ];
 #pragma unroll
         for (int j = 0; j < TJ; ++j) re[j] = im[j] = 0.0;
 #pragma unroll 4
         for (int c = 0; c < d; ++c) {
-            const double2 x = X[a * d + c];
+            const double2 x = X[a * ld + c];
 #pragma unroll
             for (int j = 0; j < TJ; ++j) {
-                const double2 y = Y[c * d + b0 + j];
+                const double2 y = Y[c * ld + b0 + j];
                 re[j] = fma(x.x, y.x, re[j]);
                 re[j] = fma(-x.y, y.y, re[j]);
                 im[j] = fma(x.x, y.y, im[j]);
@@ -149,116 +172,104 @@ __device__ __forceinline__ void cmatmul(double2* __restrict__ C, const double2* 
             }
         }
 #pragma unroll
-        for (int j = 0; j < TJ; ++j) C[a * d + b0 + j] = make_double2(re[j], im[j]);
+        for (int j = 0; j < TJ; ++j) C[a * ld + b0 + j] = make_double2(re[j], im[j]);
     }
-    __syncwarp();
+    gsync<GS>();
 }
 
-template <int N>
-__global__ void k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* __restrict__ epsp_g,
-                               const int32_t* __restrict__ counts, const double* __restrict__ rho0, int max_iter,
-                               double tol, double* __restrict__ rho_out, int32_t* __restrict__ iters,
-                               unsigned int* __restrict__ queue) {
-    constexpr int d = Axis<N>::d, D = Axis<N>::D, K6 = Axis<N>::K6;
+template <int N, int GS>
+__global__ void __launch_bounds__(GS)
+k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* __restrict__ epsp,
+               const int32_t* __restrict__ counts, const double* __restrict__ rho0, int max_iter, double tol,
+               double* __restrict__ rho_out, int32_t* __restrict__ iters, unsigned int* __restrict__ queue) {
+    constexpr int d = Axis<N>::d, D = Axis<N>::D, K6 = Axis<N>::K6, ld = Axis<N>::ld;
     extern __shared__ __align__(16) double smd[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    double* epsp = smd;  // [K6], shared by the CTA
-    double* base = smd + K6 + (size_t)warp * Axis<N>::per_warp;
-    double2* rho = reinterpret_cast<double2*>(base);
-    double2* Rm = rho + D;
-    double2* W = Rm + D;
-    double* bufA = reinterpret_cast<double*>(W + D);
+    __shared__ double red[32];
+    __shared__ unsigned int next_sample;
+    const int lane = threadIdx.x;  // index within the group (= CTA)
+    double2* rho = reinterpret_cast<double2*>(smd);    // [d][ld]
+    double2* Rm = rho + d * ld;                        // [d][ld]
+    double2* W = Rm + d * ld;                          // transform workspace (dense D) / product (padded)
+    double* bufA = reinterpret_cast<double*>(W + d * ld);
     double* bufB = bufA + K6;
     double* f = bufB + K6;
-    for (int e = threadIdx.x; e < K6; e += blockDim.x) epsp[e] = epsp_g[e];
-    __syncthreads();
-    (void)nw;
 
     for (;;) {
-        unsigned int b = 0;
-        if (lane == 0) b = atomicAdd(queue, 1u);
-        b = __shfl_sync(0xffffffffu, b, 0);
+        __syncthreads();
+        if (lane == 0) next_sample = atomicAdd(queue, 1u);
+        __syncthreads();
+        const unsigned int b = next_sample;
         if (b >= (unsigned)B) break;
         // ---- load the sample: frequencies into canonical slots, start state
         const int32_t* c = counts + (size_t)b * K;
-        long long tot = 0;
-        for (int k = lane; k < K; k += 32) tot += c[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        const double total = (double)tot;
-        for (int e = lane; e < K6; e += 32) f[e] = 0.0;
-        __syncwarp();
-        for (int k = lane; k < K; k += 32) f[slot_of_col[k]] = (double)c[k] / total;
+        long long tot_i = 0;
+        for (int k = lane; k < K; k += GS) tot_i += c[k];
+        const double total = gsum<GS>((double)tot_i, red, lane);
+        for (int e = lane; e < K6; e += GS) f[e] = 0.0;
+        gsync<GS>();
+        for (int k = lane; k < K; k += GS) f[slot_of_col[k]] = (double)c[k] / total;
         if (rho0) {
             const double2* r0 = reinterpret_cast<const double2*>(rho0) + (size_t)b * D;
-            for (int e = lane; e < D; e += 32) {  // Hermitian part of the start, as the packed kernels take it
+            for (int e = lane; e < D; e += GS) {  // Hermitian part of the start, as the packed kernels take it
                 const int a = e / d, bb = e % d;
                 const double2 z = r0[e], zt = r0[bb * d + a];
-                rho[e] = (a == bb) ? make_double2(z.x, 0.0) : (a < bb ? z : make_double2(zt.x, -zt.y));
+                rho[a * ld + bb] = (a == bb) ? make_double2(z.x, 0.0) : (a < bb ? z : make_double2(zt.x, -zt.y));
             }
         } else {
-            for (int e = lane; e < D; e += 32) rho[e] = make_double2((e / d == e % d) ? 1.0 / d : 0.0, 0.0);
+            for (int e = lane; e < D; e += GS)
+                rho[(e / d) * ld + e % d] = make_double2((e / d == e % d) ? 1.0 / d : 0.0, 0.0);
         }
-        __syncwarp();
+        gsync<GS>();
         int it = 0;
         for (it = 1; it <= max_iter; ++it) {
             // S_i = Tr(sigma_i rho)
-            for (int e = lane; e < D; e += 32) W[interleave<N>(e / d, e % d)] = rho[e];
-            __syncwarp();
-            pauli_forward<N>(W, lane);
-            for (int e = lane; e < D; e += 32) bufA[e] = W[e].x;
-            __syncwarp();
-            double* q = axis_forward_all<N>(bufA, bufB, lane);  // q[slot] = p_slot / c_slot
-            for (int e = lane; e < K6; e += 32) {
-                const double y = q[e] + epsp[e];
-                double x;
-                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(y));
-                double er = fma(-y, x, 1.0);
-                x = fma(x, er, x);
-                er = fma(-y, x, 1.0);
-                x = fma(x, er, x);
-                q[e] = f[e] * x;
-            }
-            __syncwarp();
-            double* g = axis_adjoint_all<N>(q, q == bufA ? bufB : bufA, lane);  // Pauli coefficients of R
-            for (int e = lane; e < D; e += 32) W[e] = make_double2(g[e], 0.0);
-            __syncwarp();
-            pauli_inverse<N>(W, lane);
-            for (int e = lane; e < D; e += 32) Rm[e] = W[interleave<N>(e / d, e % d)];
-            __syncwarp();
-            cmatmul<N>(W, Rm, rho, lane);   // W = R rho
-            double2* T = reinterpret_cast<double2*>(bufA);  // 2*D doubles fit in one contraction buffer (2*4^N <= 6^N for N >= 3)
-            cmatmul<N>(T, W, Rm, lane);     // T = R rho R
+            for (int e = lane; e < D; e += GS) W[interleave<N>(e / d, e % d)] = rho[(e / d) * ld + e % d];
+            gsync<GS>();
+            pauli_forward<N, GS>(W, lane);
+            for (int e = lane; e < D; e += GS) bufA[e] = W[e].x;
+            gsync<GS>();
+            double* q = axis_forward_all<N, GS>(bufA, bufB, lane);  // q[slot] = p_slot / c_slot
+            for (int e = lane; e < K6; e += GS) q[e] = f[e] * fast_recip(q[e] + epsp[e]);
+            gsync<GS>();
+            double* g = axis_adjoint_all<N, GS>(q, q == bufA ? bufB : bufA, lane);  // Pauli coefficients of R
+            for (int e = lane; e < D; e += GS) W[e] = make_double2(g[e], 0.0);
+            gsync<GS>();
+            pauli_inverse<N, GS>(W, lane);
+            for (int e = lane; e < D; e += GS) Rm[(e / d) * ld + e % d] = W[interleave<N>(e / d, e % d)];
+            gsync<GS>();
+            cmatmul<N, GS>(W, Rm, rho, lane);   // W = R rho
+            double2* T = reinterpret_cast<double2*>(bufA);  // 2*d*ld doubles fit in one contraction buffer (<= 6^N)
+            cmatmul<N, GS>(T, W, Rm, lane);     // T = R rho R
             // Hermitise, normalise, step norm
             double tr = 0.0;
-            for (int a = lane; a < d; a += 32) tr += T[a * d + a].x;
-            tr = warp_sum(tr);
+            for (int a = lane; a < d; a += GS) tr += T[a * ld + a].x;
+            tr = gsum<GS>(tr, red, lane);
             const double inv = 1.0 / tr;
             double del = 0.0;
-            for (int e = lane; e < D; e += 32) {
+            for (int e = lane; e < D; e += GS) {
                 const int a = e / d, bb = e % d;
                 double2 v;
                 if (a == bb) {
-                    v = make_double2(T[e].x * inv, 0.0);
+                    v = make_double2(T[a * ld + a].x * inv, 0.0);
                 } else {
-                    const double2 z = T[e], zt = T[bb * d + a];
+                    const double2 z = T[a * ld + bb], zt = T[bb * ld + a];
                     v = make_double2(0.5 * (z.x + zt.x) * inv, 0.5 * (z.y - zt.y) * inv);
                 }
-                const double dr = v.x - rho[e].x, di = v.y - rho[e].y;
+                const double2 old = rho[a * ld + bb];
+                const double dr = v.x - old.x, di = v.y - old.y;
                 del += dr * dr + di * di;
-                W[e] = v;
+                W[a * ld + bb] = v;
             }
-            del = sqrt(warp_sum(del));
-            __syncwarp();
-            for (int e = lane; e < D; e += 32) rho[e] = W[e];
-            __syncwarp();
+            del = sqrt(gsum<GS>(del, red, lane));
+            gsync<GS>();
+            for (int e = lane; e < D; e += GS) rho[(e / d) * ld + e % d] = W[(e / d) * ld + e % d];
+            gsync<GS>();
             if (del < tol) break;
         }
         if (it > max_iter) it = max_iter;
         double2* out = reinterpret_cast<double2*>(rho_out) + (size_t)b * D;
-        for (int e = lane; e < D; e += 32) out[e] = rho[e];
+        for (int e = lane; e < D; e += GS) out[e] = rho[(e / d) * ld + e % d];
         if (iters && lane == 0) iters[b] = it;
-        __syncwarp();
     }
 }
 
@@ -314,22 +325,21 @@ static bool detect_axis(const double* A, int n, int K, int* slot_of_col, double*
 template <int N>
 static int launch_axis(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                        double tol, double* rho, int32_t* iters, cudaStream_t st) {
-    constexpr int K6 = Axis<N>::K6;
-    const int warps = (N == 4) ? 4 : 8;
-    const size_t smem = sizeof(double) * ((size_t)K6 + (size_t)warps * Axis<N>::per_warp);
+    // one CTA of GS threads per sample: 4 CTAs (16 warps) per SM at n = 4 instead of 4 lone warps
+    constexpr int GS = (N == 4) ? 128 : 64;
+    const size_t smem = sizeof(double) * (size_t)Axis<N>::per_warp;
     QPB_REQUIRE(smem <= 227 * 1024, "axis kernel needs %zu bytes of shared memory", smem);
-    auto kern = k_mle_rrr_axis<N>;
+    auto kern = k_mle_rrr_axis<N, GS>;
     if (smem > 48 * 1024) QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem));
+    QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GS, smem));
     if (per_sm < 1) per_sm = 1;
     long blocks = (long)num_sms() * per_sm;
-    const long need = ((long)B + warps - 1) / warps;
-    if (blocks > need) blocks = need;
+    if (blocks > B) blocks = B;
     unsigned int* queue = static_cast<unsigned int*>(scratch(st, 0, sizeof(unsigned int)));
     if (!queue) return QPB_ERR_NOMEM;
     QPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), st));
-    kern<<<(int)blocks, warps * 32, smem, st>>>(plan->K, B, plan->axis_slots, plan->axis_epsp, counts, rho0, max_iter,
+    kern<<<(int)blocks, GS, smem, st>>>(plan->K, B, plan->axis_slots, plan->axis_epsp, counts, rho0, max_iter,
                                                 tol, rho, iters, queue);
     QPB_LAUNCHED("k_mle_rrr_axis");
     return QPB_OK;
