@@ -345,9 +345,10 @@ def run_ours(args, rank, local_rank, world):
             int(lib.qpb_mle_variant(plan.handle))]
         if variant == "k_mle_rrr_pauli2":
             # structured contraction: 608 FMA + 344 add/mul per iteration, counted as executed
-            flop_iter, fp64_inst_iter = 2 * 641 + 311, 952
-            flop_note = ("executed flops of the structured (Pauli-axis) iteration: 641 DFMA + 269 DADD + 42 DMUL per "
-                         "iteration (ncu op counts, profiles/README_r1.md), FMA = 2 flop")
+            flop_iter, fp64_inst_iter = 2 * 508 + 193 + 37, 738
+            flop_note = ("executed flops of the structured (Pauli-axis) iteration: 508 DFMA + 193 DADD + 37 DMUL per "
+                         "sample-iteration (ncu thread-instruction counts / 1e7 sample-iterations, "
+                         "profiles/README_r1.md), FMA = 2 flop")
         else:
             flop_iter = 4 * K * D + 16 * d**3                                # SURVEY section 8d, dense contraction
             fp64_inst_iter = flop_iter // 2 + 5 * K
