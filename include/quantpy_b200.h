@@ -124,6 +124,21 @@ QPB_API int qpb_lifp_cptp(const qpb_process_plan* plan, int B, const int32_t* co
 QPB_API int qpb_cptp_project(int n_qubits, int B, const double* choi_in, int n_iter, double tol, double* choi_out,
                      int32_t* iters, void* stream);
 
+/* ---- polytope coverage experiments (first "next" row) ---------------------
+ * Per-trial body of test_qst / test_qpt (quantpy/tomography/polytopes/verification.py:9-78): for every
+ * trial b and confidence level j, delta = count_delta(level_j, frequencies_b, n) by the bisection of
+ * quantpy/tomography/polytopes/utils.py:16-27, and inside[b,j] = min_k(freq+delta - p_true) > -1e-15.
+ * The trial's tables are either counts [B,M,O] (frequencies = clip(counts/n, 1e-15, 1-1e-15)) or already
+ * clipped frequencies freq [B,M,O]; exactly one of the two is non-NULL.  n_shots_host [M] doubles (HOST).
+ * levels [L], p_true [M*O] (may be NULL with inside_out NULL), delta_out [B,L], inside_out [B,L] bytes.
+ * clip_b: clip freq+delta to [1e-15, 1-1e-15] as test_qst does (test_qpt does not).                      */
+QPB_API int qpb_polytope_coverage(int B, int M, int O, const int32_t* counts, const double* freq,
+                          const double* n_shots_host, int L, const double* levels, const double* p_true, int clip_b,
+                          double* delta_out, unsigned char* inside_out, void* stream);
+/* conf_out[b,j] = count_confidence(deltas[j], freq[b], n)  (utils.py:4-13). */
+QPB_API int qpb_polytope_confidence(int B, int M, int O, const double* freq, const double* n_shots_host, int L,
+                            const double* deltas, double* conf_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -152,7 +152,7 @@ def test_product_package_never_imports_the_oracle():
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "quantpy_b200.h")).read()
     declared = set(re.findall(r"QPB_API\s+[\w\s\*]+?\b(qpb_\w+)\s*\(", header))
-    assert len(declared) >= 19
+    assert len(declared) >= 21
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     lib = _native.load_library()
     for name in declared:
@@ -161,6 +161,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _native.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r"\bT (qpb_\w+)", out))
     assert exported == declared
+    lib.qpb_reset_launch_count()
     assert lib.qpb_launch_count() == 0
     # argument validation happens before any CUDA call: usable without a GPU
     assert lib.qpb_distance(3, 1, None, None, 0, None, None) < 0

@@ -206,6 +206,7 @@ def main():
         "boot_c1_mle": bootstrap_case(qp, 1, "proj-set", 10000, 33, 10, "mle"),
         "process": process_cases(qp),
         "api": api_cases(qp),
+        "polytopes": polytope_cases(qp),
     }
     for name, arrays in cases.items():
         path = os.path.join(OUT, name + ".npz")
@@ -213,5 +214,49 @@ def main():
         print(f"{name}: {os.path.getsize(path)} bytes")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--polytopes" not in sys.argv:
     main()
+
+
+def polytope_cases(qp):
+    """quantpy/tomography/polytopes: deterministic pieces on reference-sampled counts, plus two seeded
+    coverage runs (Monte-Carlo figures, compared statistically)."""
+    from quantpy.tomography.polytopes import utils as putils
+    from quantpy.tomography.polytopes import verification as pver
+
+    out = {}
+    levels = np.array([0.0, 0.5, 0.9, 0.99])
+    out["levels"] = levels
+    for n, tag in ((1, "q1"), (2, "q2")):
+        rng = np.random.default_rng(40 + n)
+        rho = haar_mixed(n, rng)
+        tmg = qp.StateTomograph(qp.Qobj(rho))
+        np.random.seed(50 + n)
+        counts, deltas, confs = [], [], []
+        for _ in range(4):
+            tmg.experiment(1000)
+            counts.append(tmg.results.copy())
+            f = np.clip(tmg.results / tmg.n_measurements[:, None], 1e-15, 1 - 1e-15)
+            deltas.append([putils.count_delta(cl, f, tmg.n_measurements) for cl in levels])
+            confs.append([putils.count_confidence(d, f, tmg.n_measurements) for d in (1e-3, 0.02, 0.1)])
+        out[f"{tag}_rho"] = rho
+        out[f"{tag}_povm"] = tmg.povm_matrix
+        out[f"{tag}_n_meas"] = np.asarray(tmg.n_measurements, float)
+        out[f"{tag}_counts"] = np.array(counts)
+        out[f"{tag}_deltas"] = np.array(deltas)
+        out[f"{tag}_confs"] = np.array(confs)
+    # seeded coverage experiments (tqdm progress goes to stderr)
+    np.random.seed(60)
+    out["qst_state"] = haar_mixed(1, np.random.default_rng(61))
+    out["qst_cover"] = pver.test_qst(qp.Qobj(out["qst_state"]), levels[1:], n_measurements=1000, n_trials=300)
+    np.random.seed(62)
+    out["qpt_cover"] = pver.test_qpt(qp.channel.depolarizing(0.1, 1), levels[1:], n_measurements=1000, n_trials=100)
+    return out
+
+
+if __name__ == "__main__" and "--polytopes" in sys.argv:
+    warnings.filterwarnings("ignore")
+    arrays = polytope_cases(load_reference())
+    path = os.path.join(OUT, "polytopes.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"polytopes: {os.path.getsize(path)} bytes")
