@@ -139,6 +139,12 @@ QPB_API int qpb_polytope_coverage(int B, int M, int O, const int32_t* counts, co
 QPB_API int qpb_polytope_confidence(int B, int M, int O, const double* freq, const double* n_shots_host, int L,
                             const double* deltas, double* conf_out, void* stream);
 
+/* ---- moment intervals (second "next" row) -----------------------------
+ * mean_out[b], var_out[b] = l2_mean, l2_variance of quantpy/stats.py:5-53 for the frequency tables
+ * freq [B,P,O] with the weight tensor weights [P,O,P,O] (interval.py:89) and n_trials shots per POVM.    */
+QPB_API int qpb_l2_moments(int B, int P, int O, const double* weights, const double* freq, double n_trials,
+                   double* mean_out, double* var_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

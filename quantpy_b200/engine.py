@@ -231,6 +231,25 @@ def cptp_project(choi_matrices, n_qubits, n_iter=1000, tol=1e-12):
     return out, iters
 
 
+def l2_moments(frequencies, n_trials, weights):
+    """(mean, variance) of the weighted squared l2 error (quantpy/stats.py:5-53) on the GPU.
+    frequencies [P, O] or [B, P, O]; weights [P, O, P, O] -> floats or arrays of length B."""
+    torch = nt.torch_cuda()
+    lib = nt.load_library()
+    f = np.asarray(frequencies, dtype=np.float64)
+    single = f.ndim == 2
+    f3 = f[None] if single else f
+    B, P, O = f3.shape
+    w = nt.to_device(np.asarray(weights, dtype=np.float64).reshape(P, O, P, O), torch.float64)
+    fd = nt.to_device(f3, torch.float64)
+    mean = torch.empty((B,), dtype=torch.float64, device="cuda")
+    var = torch.empty((B,), dtype=torch.float64, device="cuda")
+    nt.check(lib.qpb_l2_moments(B, P, O, nt.ptr(w), nt.ptr(fd), float(n_trials), nt.ptr(mean), nt.ptr(var),
+                                nt.stream_ptr()))
+    m, v = mean.cpu().numpy(), var.cpu().numpy()
+    return (float(m[0]), float(v[0])) if single else (m, v)
+
+
 _PLAN_CACHE = {}
 
 

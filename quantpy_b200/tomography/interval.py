@@ -62,6 +62,55 @@ class ConfidenceInterval(ABC):
         self.cl_to_dist = parallel.quantile_function(self.dist, presorted=True)
 
 
+class MomentInterval(ConfidenceInterval):
+    def __init__(self, tmg, distr_type="gamma"):
+        """Analytic interval from the first two moments of the squared estimation error
+        (quantpy/tomography/interval.py:59-110).  distr_type: 'gamma' | 'norm' | 'exp'."""
+        super().__init__(tmg, **_pop_hidden_keys(locals()))
+
+    def setup(self):
+        import scipy.stats as sts
+
+        from ..geometry import hs_dst, trace_dst
+        from ..routines import _left_inv
+
+        if self.mode == Mode.STATE:
+            dim = 2**self.tmg.state.n_qubits
+            n_measurements = self.tmg.n_measurements
+            frequencies = self.tmg.results / n_measurements[:, None]
+            povm = np.asarray(self.tmg.povm_matrix, dtype=np.float64)
+            inv = _left_inv(povm.reshape(-1, povm.shape[-1])) / dim
+        else:
+            dim = 4**self.tmg.channel.n_qubits
+            first = self.tmg.tomographs[0]
+            n_measurements = first.n_measurements
+            frequencies = np.vstack([t.results / n_measurements[:, None] for t in self.tmg.tomographs])
+            povm = np.asarray(first.povm_matrix, dtype=np.float64)
+            flat = povm.reshape(-1, povm.shape[-1])
+            states = np.asarray([rho.T.bloch for rho in self.tmg.input_basis.elements])
+            chan = np.einsum("sd,pi->spdi", states, flat).reshape(len(states) * len(flat), -1)
+            inv = _left_inv(chan) / dim
+        inv = inv.reshape(inv.shape[0], frequencies.shape[0], frequencies.shape[1])
+        weights = np.einsum("aij,akl->ijkl", inv, inv)  # one-time set-up on the host
+        self.mean, self.variance = engine.l2_moments(frequencies, n_measurements[0], weights)  # qpb_l2_moments
+        if self.distr_type == "norm":
+            distr = sts.norm(loc=self.mean, scale=np.sqrt(self.variance))
+        elif self.distr_type == "gamma":
+            scale = self.variance / self.mean
+            distr = sts.gamma(a=self.mean / scale, scale=scale)
+        elif self.distr_type == "exp":
+            distr = sts.expon(scale=self.mean)
+        else:
+            raise NotImplementedError(f"Unsupported distribution type {self.distr_type}")
+        if self.tmg.dst == hs_dst:
+            alpha = np.sqrt(dim / 2)
+        elif self.tmg.dst == trace_dst:
+            alpha = dim / 2
+        else:
+            raise NotImplementedError()
+        self.cl_to_dist = lambda cl: np.sqrt(distr.ppf(cl)) * alpha
+
+
 class BootstrapStateInterval(ConfidenceInterval):
     def __init__(self, tmg, n_points=1000, method="lin", physical=True, init="lin", tol=1e-3, max_iter=100,
                  state=None):
@@ -169,7 +218,6 @@ def _out_of_scope(name):
     return _Unavailable
 
 
-MomentInterval = _out_of_scope("MomentInterval")
 MomentFidelityStateInterval = _out_of_scope("MomentFidelityStateInterval")
 MomentFidelityProcessInterval = _out_of_scope("MomentFidelityProcessInterval")
 SugiyamaInterval = _out_of_scope("SugiyamaInterval")

@@ -207,6 +207,7 @@ def main():
         "process": process_cases(qp),
         "api": api_cases(qp),
         "polytopes": polytope_cases(qp),
+        "moments": moment_cases(qp),
     }
     for name, arrays in cases.items():
         path = os.path.join(OUT, name + ".npz")
@@ -214,7 +215,7 @@ def main():
         print(f"{name}: {os.path.getsize(path)} bytes")
 
 
-if __name__ == "__main__" and "--polytopes" not in sys.argv:
+if __name__ == "__main__" and "--polytopes" not in sys.argv and "--moments" not in sys.argv:
     main()
 
 
@@ -260,3 +261,45 @@ if __name__ == "__main__" and "--polytopes" in sys.argv:
     path = os.path.join(OUT, "polytopes.npz")
     np.savez_compressed(path, **arrays)
     print(f"polytopes: {os.path.getsize(path)} bytes")
+
+
+def moment_cases(qp):
+    """quantpy/stats.py moments and MomentInterval quantiles on reference-sampled counts."""
+    from quantpy import stats as qstats
+
+    out = {"levels": np.array([0.1, 0.5, 0.9, 0.99])}
+    for n, povm, tag in ((1, "proj-set", "s1"), (2, "proj-set", "s2"), (2, "proj", "s2p")):
+        rho = haar_mixed(n, np.random.default_rng(70 + n))
+        tmg = qp.StateTomograph(qp.Qobj(rho))
+        np.random.seed(71 + n)
+        tmg.experiment(2000, povm)
+        freq = tmg.results / tmg.n_measurements[:, None]
+        out[f"{tag}_povm"], out[f"{tag}_counts"], out[f"{tag}_n_meas"] = tmg.povm_matrix, tmg.results, np.asarray(tmg.n_measurements, float)
+        out[f"{tag}_identity"] = np.array([qstats.l2_mean(freq, 2000), qstats.l2_variance(freq, 2000)])
+        for distr in ("gamma", "norm", "exp"):
+            itv = qp.MomentInterval(tmg, distr_type=distr)
+            itv.setup()
+            out[f"{tag}_{distr}"] = itv.cl_to_dist(out["levels"])
+        tmg_tr = qp.StateTomograph(qp.Qobj(rho), dst="trace")
+        tmg_tr.povm_matrix, tmg_tr.results = tmg.povm_matrix, tmg.results
+        tmg_tr.n_measurements = tmg.n_measurements
+        itv = qp.MomentInterval(tmg_tr)
+        itv.setup()
+        out[f"{tag}_gamma_trace"] = itv.cl_to_dist(out["levels"])
+    chan = qp.channel.depolarizing(0.1, 1)
+    ptmg = qp.ProcessTomograph(chan, input_states="sic")
+    np.random.seed(75)
+    ptmg.experiment(2000, "proj-set")
+    itv = qp.MomentInterval(ptmg)
+    itv.setup()
+    out["p1_counts"] = ptmg.results
+    out["p1_gamma"] = itv.cl_to_dist(out["levels"])
+    return out
+
+
+if __name__ == "__main__" and "--moments" in sys.argv:
+    warnings.filterwarnings("ignore")
+    arrays = moment_cases(load_reference())
+    path = os.path.join(OUT, "moments.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"moments: {os.path.getsize(path)} bytes")
