@@ -124,6 +124,15 @@ QPB_API int qpb_lifp_cptp(const qpb_process_plan* plan, int B, const int32_t* co
 QPB_API int qpb_cptp_project(int n_qubits, int B, const double* choi_in, int n_iter, double tol, double* choi_out,
                      int32_t* iters, void* stream);
 
+/* 'states' process estimate (process.py:316-327): choi[b] = sum_s G_s (x) rho[b,s] from reconstructed output
+ * states rho [B,S,d,d] and the input-basis coefficients G [S,d,d] (all complex128), followed by the conditional
+ * projection: matrices that already satisfy Channel.is_cptp(atol) (channel.py:144-157) are returned unchanged
+ * with iters = 0, the others go through the alternating projection.  (third "next" row.) */
+QPB_API int qpb_choi_from_states(int n_qubits, int S, int B, const double* G, const double* rho, double* choi,
+                         void* stream);
+QPB_API int qpb_cptp_project_if_needed(int n_qubits, int B, const double* choi_in, int n_iter, double tol, double atol,
+                               double* choi_out, int32_t* iters, void* stream);
+
 /* ---- polytope coverage experiments (first "next" row) ---------------------
  * Per-trial body of test_qst / test_qpt (quantpy/tomography/polytopes/verification.py:9-78): for every
  * trial b and confidence level j, delta = count_delta(level_j, frequencies_b, n) by the bisection of

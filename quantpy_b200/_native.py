@@ -45,6 +45,8 @@ SIGNATURES = {
     "qpb_bootstrap_state_workspace": (ctypes.c_size_t, [_vp, _int, _int, _int]),
     "qpb_bootstrap_state": (_int, [_vp, _int, _int, _int, _vp, _vp, _u64, _u64, _int, _int, _int, _int, _dbl,
                                    _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "qpb_choi_from_states": (_int, [_int, _int, _int, _vp, _vp, _vp, _vp]),
+    "qpb_cptp_project_if_needed": (_int, [_int, _int, _vp, _int, _dbl, _dbl, _vp, _vp, _vp]),
     "qpb_polytope_coverage": (_int, [_int, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _int, _vp, _vp, _vp]),
     "qpb_polytope_confidence": (_int, [_int, _int, _int, _vp, _vp, _int, _vp, _vp, _vp]),
     "qpb_l2_moments": (_int, [_int, _int, _int, _vp, _vp, _dbl, _vp, _vp, _vp]),

@@ -55,13 +55,38 @@ __global__ void k_lifp(int S, int K, int ss, int B, const double* __restrict__ L
     }
 }
 
+// 'states' assembly (process.py:316-324): choi[b] = sum_s G_s (x) rho[b][s], with G_s[i][j] the coefficient of input
+// state s in the decomposition of the matrix unit E_ij (basis.py:31-34).  One thread per Choi entry.
+__global__ void k_choi_from_states(int d, int S, int B, const double* __restrict__ G, const double* __restrict__ rho,
+                                   double* __restrict__ choi) {
+    const int s = d * d;
+    const long total = (long)B * s * s;
+    const cplx* Gc = reinterpret_cast<const cplx*>(G);
+    const cplx* rc = reinterpret_cast<const cplx*>(rho);
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long b = t / (s * s);
+        const int e = (int)(t % (s * s)), r = e / s, c = e % s;
+        const int i = r / d, a = r % d, j = c / d, bb = c % d;
+        double re = 0.0, im = 0.0;
+        for (int k = 0; k < S; ++k) {
+            const cplx g = Gc[(k * d + i) * d + j], z = rc[((b * S + k) * d + a) * d + bb];
+            re += g.re * z.re - g.im * z.im;
+            im += g.re * z.im + g.im * z.re;
+        }
+        choi[2 * t] = re;
+        choi[2 * t + 1] = im;
+    }
+}
+
 __host__ __device__ inline size_t cptp_smem_per_warp(int s) {
     return sizeof(cplx) * (5 * (size_t)s * s + 2 * (size_t)s * jacobi_ld(s)) + sizeof(jrot) * (size_t)(s / 2 + 1) +
            sizeof(cplx) * 16;
 }
 
 // Alternating projection of process.py:237-257, one warp per Choi matrix.
-__global__ void k_cptp(int d, int B, const double* __restrict__ choi_in, int n_iter, double tol,
+// check_atol >= 0: first test Channel.is_cptp(atol) (quantpy/channel.py:144-157) and leave matrices that pass
+// untouched (iters = 0), as ProcessTomograph._point_estimate_states does (process.py:325-326).
+__global__ void k_cptp(int d, int B, const double* __restrict__ choi_in, int n_iter, double tol, double check_atol,
                        double* __restrict__ choi_out, int32_t* __restrict__ iters) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int s = d * d, ss = s * s;
@@ -88,6 +113,41 @@ __global__ void k_cptp(int d, int B, const double* __restrict__ choi_in, int n_i
             y[e].re = y[e].im = 0.0;
         }
         __syncwarp();
+        if (check_atol >= 0.0) {
+            // trace preserving: |Tr_out x - I| <= atol + 1e-5 |I| elementwise (np.allclose)
+            double bad = 0.0;
+            for (int e = lane; e < d * d; e += 32) {
+                const int i = e / d, j = e % d;
+                double re = 0.0, im = 0.0;
+                for (int a = 0; a < d; ++a) {
+                    const cplx z = x[(i * d + a) * s + (j * d + a)];
+                    re += z.re;
+                    im += z.im;
+                }
+                const double target = (i == j) ? 1.0 : 0.0;
+                const double dev = sqrt((re - target) * (re - target) + im * im);
+                if (dev > check_atol + 1e-5 * target) bad = 1.0;
+            }
+            // completely positive: eigenvalues >= -atol
+            for (int e = lane; e < ss; e += 32) {
+                const int r = e / s, c = e % s, et = c * s + r;
+                A[r * ld + c].re = 0.5 * (x[e].re + x[et].re);
+                A[r * ld + c].im = 0.5 * (x[e].im - x[et].im);
+            }
+            __syncwarp();
+            warp_jacobi<false>(A, V, rot, s, lane);
+            for (int j = lane; j < s; j += 32)
+                if (A[j * ld + j].re < -check_atol) bad = 1.0;
+            bad = warp_max(bad);
+            __syncwarp();
+            if (bad == 0.0) {
+                cplx* dst0 = reinterpret_cast<cplx*>(choi_out) + b * ss;
+                for (int e = lane; e < ss; e += 32) dst0[e] = x[e];
+                if (iters && lane == 0) iters[b] = 0;
+                __syncwarp();
+                continue;
+            }
+        }
         int it = 0;
         for (it = 1; it <= n_iter; ++it) {
             // ---- y' = TP(x + p) = t + ((I - Tr_out t) (x) I) / d
@@ -171,8 +231,8 @@ __global__ void k_cptp(int d, int B, const double* __restrict__ choi_in, int n_i
     }
 }
 
-static int launch_cptp(int n, int B, const double* in, int n_iter, double tol, double* out, int32_t* iters,
-                       cudaStream_t st) {
+static int launch_cptp(int n, int B, const double* in, int n_iter, double tol, double check_atol, double* out,
+                       int32_t* iters, cudaStream_t st) {
     const int d = 1 << n, s = d * d;
     const int warps = (s >= 16) ? 4 : 8;
     const size_t smem = warps * cptp_smem_per_warp(s);
@@ -181,7 +241,7 @@ static int launch_cptp(int n, int B, const double* in, int n_iter, double tol, d
     long blocks = ((long)B + warps - 1) / warps;
     const long cap = (long)num_sms() * (s >= 16 ? 1 : 4);
     if (blocks > cap) blocks = cap;
-    k_cptp<<<(int)blocks, warps * 32, smem, st>>>(d, B, in, n_iter, tol, out, iters);
+    k_cptp<<<(int)blocks, warps * 32, smem, st>>>(d, B, in, n_iter, tol, check_atol, out, iters);
     QPB_LAUNCHED("k_cptp");
     return QPB_OK;
 }
@@ -247,7 +307,7 @@ int qpb_lifp_cptp(const qpb_process_plan* plan, int B, const int32_t* counts, in
         k_lifp<<<(int)blocks, warps * 32, smem, st>>>(plan->S, plan->K, plan->d4, B, plan->LinvT, counts, choi);
         QPB_LAUNCHED("k_lifp");
     }
-    if (cptp) return launch_cptp(plan->n, B, choi, n_iter, tol, choi, iters, st);
+    if (cptp) return launch_cptp(plan->n, B, choi, n_iter, tol, -1.0, choi, iters, st);
     if (iters) QPB_CUDA(cudaMemsetAsync(iters, 0, sizeof(int32_t) * (size_t)B, st));
     return QPB_OK;
 }
@@ -258,7 +318,27 @@ int qpb_cptp_project(int n_qubits, int B, const double* choi_in, int n_iter, dou
     QPB_REQUIRE(B >= 0 && n_iter >= 0, "bad arguments");
     if (B == 0) return QPB_OK;
     QPB_REQUIRE(choi_in && choi_out, "NULL buffer");
-    return launch_cptp(n_qubits, B, choi_in, n_iter, tol, choi_out, iters, (cudaStream_t)stream);
+    return launch_cptp(n_qubits, B, choi_in, n_iter, tol, -1.0, choi_out, iters, (cudaStream_t)stream);
+}
+
+int qpb_cptp_project_if_needed(int n_qubits, int B, const double* choi_in, int n_iter, double tol, double atol,
+                               double* choi_out, int32_t* iters, void* stream) {
+    QPB_REQUIRE(n_qubits >= 1 && n_qubits <= 2, "CPTP projection supports 1 or 2 qubits (got %d)", n_qubits);
+    QPB_REQUIRE(B >= 0 && n_iter >= 0 && atol >= 0.0, "bad arguments");
+    if (B == 0) return QPB_OK;
+    QPB_REQUIRE(choi_in && choi_out, "NULL buffer");
+    return launch_cptp(n_qubits, B, choi_in, n_iter, tol, atol, choi_out, iters, (cudaStream_t)stream);
+}
+
+int qpb_choi_from_states(int n_qubits, int S, int B, const double* G, const double* rho, double* choi, void* stream) {
+    QPB_REQUIRE(n_qubits >= 1 && n_qubits <= 2 && S >= 1 && B >= 0, "bad arguments");
+    if (B == 0) return QPB_OK;
+    QPB_REQUIRE(G && rho && choi, "NULL buffer");
+    const int d = 1 << n_qubits;
+    const long total = (long)B * d * d * d * d;
+    k_choi_from_states<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, S, B, G, rho, choi);
+    QPB_LAUNCHED("k_choi_from_states");
+    return QPB_OK;
 }
 
 }  // extern "C"

@@ -231,6 +231,31 @@ def cptp_project(choi_matrices, n_qubits, n_iter=1000, tol=1e-12):
     return out, iters
 
 
+def choi_from_states(G, rho, n_qubits):
+    """choi[b] = sum_s G_s (x) rho[b, s]: G host complex [S, d, d]; rho device [B, S, d, d, 2] -> device [B, d^2, d^2, 2]."""
+    torch = nt.torch_cuda()
+    lib = nt.load_library()
+    B, S = rho.shape[0], rho.shape[1]
+    s = 4**n_qubits
+    Gd = nt.complex_to_device(np.asarray(G, dtype=np.complex128))
+    choi = torch.empty((B, s, s, 2), dtype=torch.float64, device="cuda")
+    nt.check(lib.qpb_choi_from_states(n_qubits, S, B, nt.ptr(Gd), nt.ptr(rho.contiguous()), nt.ptr(choi),
+                                      nt.stream_ptr()))
+    return choi
+
+
+def cptp_project_if_needed(choi, n_qubits, n_iter=1000, tol=1e-12, atol=1e-5):
+    """Device Choi batch -> (projected batch, iters); matrices passing Channel.is_cptp(atol) are left untouched."""
+    torch = nt.torch_cuda()
+    lib = nt.load_library()
+    B = choi.shape[0]
+    out = torch.empty_like(choi)
+    iters = torch.empty((B,), dtype=torch.int32, device="cuda")
+    nt.check(lib.qpb_cptp_project_if_needed(n_qubits, B, nt.ptr(choi.contiguous()), int(n_iter), float(tol),
+                                            float(atol), nt.ptr(out), nt.ptr(iters), nt.stream_ptr()))
+    return out, iters
+
+
 def l2_moments(frequencies, n_trials, weights):
     """(mean, variance) of the weighted squared l2 error (quantpy/stats.py:5-53) on the GPU.
     frequencies [P, O] or [B, P, O]; weights [P, O, P, O] -> floats or arrays of length B."""

@@ -190,16 +190,17 @@ class BootstrapProcessInterval(ConfidenceInterval):
                 local = torch.tensor([float(self.tmg.dst(Qobj(c), self.channel.choi))
                                       for c in nt.complex_to_host(choi)], dtype=torch.float64, device="cuda")
         else:
-            counts = boot.sample_counts(hi - lo, first.n_measurements, first.povm_matrix, seed, lo)
+            counts = boot.sample_counts(hi - lo, first.n_measurements, first.povm_matrix, seed, lo, device=True)
             boot.experiment(first.n_measurements, first.povm_matrix)
-            vals = []
-            for table in counts:
-                boot.results = table
-                est = boot.point_estimate(method="states", states_est_method=self.states_est_method,
-                                          states_physical=self.states_physical, states_init=self.states_init,
-                                          cptp=self.cptp)
-                vals.append(float(self.tmg.dst(est.choi, self.channel.choi)))
-            local = torch.tensor(vals, dtype=torch.float64, device="cuda")
+            choi = boot.point_estimate_states_batch(counts, cptp=self.cptp, method=self.states_est_method,
+                                                    physical=self.states_physical, init=self.states_init, device=True)
+            if kind is not None:
+                local = engine.distance(choi, centre, kind)
+            else:
+                from ..qobj import Qobj
+
+                local = torch.tensor([float(self.tmg.dst(Qobj(c), self.channel.choi))
+                                      for c in nt.complex_to_host(choi)], dtype=torch.float64, device="cuda")
         self._finish(local, self.n_points)
 
 

@@ -18,7 +18,7 @@ from ..basis import Basis
 from ..channel import Channel
 from ..measurements import generate_measurement_matrix
 from ..qobj import Qobj
-from ..routines import _left_inv, _out_ptrace_oper, generate_pauli, generate_single_entries, kron
+from ..routines import _left_inv, _out_ptrace_oper, generate_pauli, generate_single_entries
 from .state import StateTomograph, resolve_dst
 
 
@@ -155,15 +155,35 @@ class ProcessTomograph:
         self.reconstructed_channel = Channel(choi)
         return self.reconstructed_channel
 
+    def point_estimate_states_batch(self, counts, cptp=True, method="lin", physical=True, init="lin", n_iter=1000,
+                                    tol=1e-10, return_iters=False, device=False):
+        """'states' estimates (process.py:316-327) for a batch of count tables [B, S, P, O]: every output state is
+        reconstructed by the state kernels (B*S samples in one launch), the Choi matrices are assembled on the
+        device as sum_s G_s (x) rho_s (G_s = coefficients of the matrix units in the input basis), and those that
+        fail Channel.is_cptp (atol 1e-5) go through the alternating projection."""
+        torch = nt.torch_cuda()
+        if method == "mle-constr":
+            raise NotImplementedError("'mle-constr' (SLSQP) is outside the B200 hot path; use 'mle'")
+        first = self.tomographs[0]
+        plan = engine.state_plan(first.povm_matrix, first.n_measurements)
+        S = len(self.tomographs)
+        if not torch.is_tensor(counts):
+            counts = nt.to_device(np.asarray(counts).reshape(-1, S, plan.K), torch.int32)
+        B = counts.shape[0]
+        # the reference forwards (n_iter, tol) positionally as (max_iter, tol) of the state estimator (process.py:317)
+        rho, _ = plan.estimate(counts.reshape(B * S, plan.K), method, physical, init, n_iter, tol)
+        d = 2**self.channel.n_qubits
+        G = np.transpose(self._decomposed_single_entries.reshape(d, d, S), (2, 0, 1))
+        choi = engine.choi_from_states(G, rho.reshape(B, S, d, d, 2), self.channel.n_qubits)
+        iters = torch.zeros((B,), dtype=torch.int32, device="cuda")
+        if cptp:
+            choi, iters = engine.cptp_project_if_needed(choi, self.channel.n_qubits)
+        if device:
+            return (choi, iters) if return_iters else choi
+        out = nt.complex_to_host(choi)
+        return (out, iters.cpu().numpy()) if return_iters else out
+
     def _point_estimate_states(self, cptp, method, physical, init, n_iter, tol):
-        # the reference forwards (n_iter, tol) positionally into StateTomograph.point_estimate (process.py:317)
-        outputs = [tmg.point_estimate(method, physical, init, n_iter, tol) for tmg in self.tomographs]
-        output_basis = Basis(outputs)
-        dim = output_basis.dim
-        choi = Qobj(np.zeros((dim, dim), dtype=np.complex128))
-        for coefs in self._decomposed_single_entries:
-            choi += kron(self.input_basis.compose(coefs), output_basis.compose(coefs))
+        choi = self.point_estimate_states_batch(self.results[None], cptp, method, physical, init, n_iter, tol)[0]
         self.reconstructed_channel = Channel(choi)
-        if cptp and not self.reconstructed_channel.is_cptp(verbose=False):
-            self.reconstructed_channel = self.cptp_projection(self.reconstructed_channel)
         return self.reconstructed_channel

@@ -311,3 +311,32 @@ def test_config5_process_bootstrap_full_size(qp, n, B):
     itv = qp.BootstrapProcessInterval(tmg, n_points=B // 2, channel=chan)
     itv.setup(seed=3)
     assert np.all(np.diff(itv.dist) >= 0) and itv.dist[0] > 0
+
+
+@pytest.mark.parametrize("n,method", [(1, "lin"), (1, "mle"), (2, "lin")])
+def test_process_states_method_batched(qp, golden, n, method):
+    """'states' estimates with per-state reconstructions batched on the state kernels, Choi
+    assembly and conditional CPTP projection on the device, against the oracle's restatement of process.py:316-327."""
+    g = golden("process")
+    tmg = process_tomograph(qp, g, n)
+    counts = g[f"dep{n}_counts"]
+    if method == "lin":
+        tmg.results = counts[0]
+        one = tmg.point_estimate("states", cptp=True)
+        assert fro(one.choi.matrix, g[f"dep{n}_states_cptp"][0]) < 1e-9  # reference output
+    inputs = oproc.input_states("sic", n)
+    pm, n_meas = g[f"dep{n}_povm"], g[f"dep{n}_n_meas"]
+    more = tmg.sample_counts(6, 10000, "proj-set", seed=4)
+    kw = dict(max_iter=30, tol=1e-6)
+    for cptp in (False, True):
+        got, iters = tmg.point_estimate_states_batch(more, cptp=cptp, method=method, n_iter=30, tol=1e-6,
+                                                     return_iters=True)
+        for b in range(len(more)):
+            want = oproc.states_estimate(more[b], inputs, pm, n_meas, cptp=cptp, method=method, mle="rrr", **kw)
+            assert fro(got[b], want) < 1e-9
+            assert (iters[b] == 0) == (not cptp or oproc.is_cptp(oproc.states_estimate(
+                more[b], inputs, pm, n_meas, cptp=False, method=method, mle="rrr", **kw)))
+    itv = qp.BootstrapProcessInterval(tmg, n_points=300, method="states", states_est_method=method,
+                                      channel=tmg.channel)
+    itv.setup(seed=1)
+    assert itv.dist.shape == (300,) and np.all(np.diff(itv.dist) >= 0) and itv.dist[0] > 0
