@@ -30,6 +30,16 @@ static int max_blocks_per_sm() {
 }
 #define kMaxBlocksPerSm max_blocks_per_sm()
 
+// 1/y to within an ulp: hardware seed x0 (relative error e <= 2^-23) and one third-order correction
+// x0 (1 + e + e^2), truncation e^3 <= 2^-69 -- three FMAs on the FP64 pipe.
+__device__ __forceinline__ double fast_rcp(double y) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(y));
+    const double e = fma(-y, x, 1.0);
+    const double t = fma(e, e, e);
+    return fma(x, t, x);
+}
+
 template <int d>
 struct Packed {
     // z = H(a, b) of a packed Hermitian array with compile-time indices
@@ -165,7 +175,7 @@ k_mle_rrr_small(int K, int B, const double* __restrict__ Ar, const int32_t* __re
                         p0 = fma(row[e], h2[e], p0);
                         p1 = fma(row[e + 1], h2[e + 1], p1);
                     }
-                    const double w = fs[k * kSmallThreads + tid] / ((p0 + p1) + kLogGuard);
+                    const double w = fs[k * kSmallThreads + tid] * fast_rcp((p0 + p1) + kLogGuard);
 #pragma unroll
                     for (int e = 0; e < D; ++e) R[e] = fma(w, row[e], R[e]);
                 }
@@ -174,7 +184,7 @@ k_mle_rrr_small(int K, int B, const double* __restrict__ Ar, const int32_t* __re
                 double tr = 0.0;
 #pragma unroll
                 for (int a = 0; a < d; ++a) tr += hn[a * d + a];
-                const double inv = 1.0 / tr;
+                const double inv = fast_rcp(tr);
                 double del = 0.0;
 #pragma unroll
                 for (int e = 0; e < D; ++e) {
@@ -219,15 +229,6 @@ struct ConstTables {
     double tab2[K * (1 << (2 * N))];
 };
 
-// 1/y to within an ulp: hardware seed x0 (relative error e <= 2^-23) and one third-order correction
-// x0 (1 + e + e^2), truncation e^3 <= 2^-69 -- three FMAs on the FP64 pipe.
-__device__ __forceinline__ double fast_rcp(double y) {
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(y));
-    const double e = fma(-y, x, 1.0);
-    const double t = fma(e, e, e);
-    return fma(x, t, x);
-}
 
 template <int N, int K>
 __global__ void __launch_bounds__(kSmallThreads)

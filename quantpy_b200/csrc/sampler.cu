@@ -259,7 +259,7 @@ __global__ void k_multinomial_binomial(int B, int P, int O, const double* __rest
         bool flip = false, ready = false;
         int o = 0;
         while (o + 1 < O) {
-            if (!ready) {
+            if (!ready) {  // set up the lane's next binomial, then fall through to its first proposal
                 po = fmin(fmax(row[o], 0.0), 1.0);
                 long c = -1;
                 if (left <= 0 || !(po > 0.0)) {
@@ -283,16 +283,17 @@ __global__ void k_multinomial_binomial(int B, int P, int O, const double* __rest
                     mass -= po;
                     ++o;
                 }
-                continue;
             }
-            const long y = st.propose(rng);
-            if (y >= 0) {
-                const long c = flip ? left - y : y;
-                out[o] = (int32_t)c;
-                left -= c;
-                mass -= po;
-                ++o;
-                ready = false;
+            if (ready) {
+                const long y = st.propose(rng);
+                if (y >= 0) {
+                    const long c = flip ? left - y : y;
+                    out[o] = (int32_t)c;
+                    left -= c;
+                    mass -= po;
+                    ++o;
+                    ready = false;
+                }
             }
         }
         out[O - 1] = (int32_t)left;
@@ -319,9 +320,9 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
     long max_shots = 0;
     for (int m = 0; m < P; ++m) max_shots = shots.n[m] > max_shots ? shots.n[m] : max_shots;
     const char* force = getenv("QPB_SAMPLER");
-    // measured on B200 (tools/bench_configs.py): the binomial chain is sequential in O (0.018 ms per outcome at
+    // measured on B200 (tools/bench_configs.py): the binomial chain is sequential in O (0.0084 ms per outcome at
     // 1e5 threads) while the alias kernel scales with the shots (1.2 ms per 1e4 shots x 1e5 warps)
-    bool use_binomial = max_shots > 128L * O;
+    bool use_binomial = max_shots > 64L * O;
     if (force && force[0] == 'a') use_binomial = false;
     if (force && force[0] == 'b') use_binomial = true;
     if (use_binomial) {
