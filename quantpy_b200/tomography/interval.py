@@ -148,8 +148,13 @@ class BootstrapStateInterval(ConfidenceInterval):
                                  device="cuda")
         else:
             local = out["dist"]
-        self.iters = out["iters"].cpu().numpy()
+        self._iters_dev = out["iters"]  # copied to the host only if someone asks (see `iters`)
         self._finish(local, self.n_points)
+
+    @property
+    def iters(self):
+        """R.rho.R iteration count of every local bootstrap sample (zeros for 'lin')."""
+        return self._iters_dev.cpu().numpy()
 
 
 class BootstrapProcessInterval(ConfidenceInterval):
