@@ -220,6 +220,64 @@ __global__ void k_lin_project(int n, int K, int B, const double* __restrict__ Lh
     }
 }
 
+// Projection of already-inverted packed states h_in [B][d*d] (from the DMMA GEMM): G lanes per sample, 32/G samples
+// per warp (group_jacobi).  shared per group: A, V (d x ld complex) and d/2 rotations.
+__host__ __device__ inline size_t project_smem_per_group(int d) {
+    return sizeof(cplx) * 2 * (size_t)d * jacobi_ld(d) + sizeof(jrot) * (size_t)(d / 2 + 1);
+}
+
+template <int G>
+__global__ void k_project_packed(int d, int B, const double* __restrict__ h_in, int physical, double* __restrict__ rho) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int dd = d * d, ld = jacobi_ld(d);
+    const int groups_per_block = blockDim.x / G;
+    const int grp = threadIdx.x / G, gl = threadIdx.x % G;
+    unsigned char* base = smraw + (size_t)grp * project_smem_per_group(d);
+    cplx* A = reinterpret_cast<cplx*>(base);
+    cplx* V = A + d * ld;
+    jrot* rot = reinterpret_cast<jrot*>(V + d * ld);
+    const long stride = (long)gridDim.x * groups_per_block;
+    const long first = (long)blockIdx.x * groups_per_block + grp;
+    const long rounds = (B + stride - 1) / stride;  // every group runs the same number of rounds (warp-wide syncs)
+    for (long r = 0; r < rounds; ++r) {
+        const long b = first + r * stride;
+        const bool valid = b < B;
+        if (valid) {
+            const double* h = h_in + b * dd;
+            for (int e = gl; e < dd; e += G) A[(e / d) * ld + e % d] = herm_get(h, d, e / d, e % d);
+        }
+        __syncwarp();
+        double* out = rho + b * 2 * dd;
+        if (!physical) {
+            if (valid)
+                for (int e = gl; e < dd; e += G) {
+                    out[2 * e] = A[(e / d) * ld + e % d].re;
+                    out[2 * e + 1] = A[(e / d) * ld + e % d].im;
+                }
+        } else {
+            group_jacobi<true, G>(A, V, rot, d, gl, valid);
+            if (valid) {
+                double tr = 0.0;
+                for (int j = 0; j < d; ++j) tr += fmax(A[j * ld + j].re, kClipState);
+                const double inv = 1.0 / tr;
+                for (int e = gl; e < dd; e += G) {
+                    const int a = e / d, bb = e % d;
+                    double re = 0.0, im = 0.0;
+                    for (int j = 0; j < d; ++j) {
+                        const double lam = fmax(A[j * ld + j].re, kClipState);
+                        const cplx x = V[a * ld + j], y = V[bb * ld + j];
+                        re += lam * (x.re * y.re + x.im * y.im);
+                        im += lam * (x.im * y.re - x.re * y.im);
+                    }
+                    out[2 * e] = re * inv;
+                    out[2 * e + 1] = im * inv;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Generic R.rho.R maximum likelihood (any n <= 4): one warp per sample, state in shared memory.
 // shared per warp: f[K] | w[K] | h[dd] | h2[dd] | Rh[dd] | hn[dd] | S[dd] cplx
@@ -453,6 +511,21 @@ int launch_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts,
         rc = launch_gemm_counts(B, plan->D, plan->K, plan->K, counts, plan->LhT, H, st);
         if (rc != QPB_OK) return rc;
         h_in = H;
+    }
+    if (h_in && plan->d == 8 && !getenv("QPB_NO_PACKED_JACOBI")) {
+        // 4 samples per warp, G = d = 8 lanes each (measured: 2.0 -> 1.35 ms per 1e5 matrices; at d = 16 two
+        // matrices per warp were slower than one, 2.2 vs 1.9 ms per 1e4, so n = 4 keeps the warp-per-matrix kernel)
+        const int d = plan->d;
+        const int threads = 256, groups = threads / d;
+        const size_t psmem = groups * project_smem_per_group(d);
+        auto kern = (d == 8) ? k_project_packed<8> : k_project_packed<16>;
+        if (psmem > 48 * 1024) QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+        long blocks = ((long)B + groups - 1) / groups;
+        const long cap = (long)num_sms() * 4;
+        if (blocks > cap) blocks = cap;
+        kern<<<(int)blocks, threads, psmem, st>>>(d, B, h_in, physical, rho);
+        QPB_LAUNCHED("k_project_packed");
+        return QPB_OK;
     }
     k_lin_project<<<grid, warps * 32, smem, st>>>(plan->n, plan->K, B, plan->LhT, counts, h_in, physical, rho);
     QPB_LAUNCHED("k_lin_project");
