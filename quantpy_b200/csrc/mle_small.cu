@@ -363,7 +363,7 @@ template <int N, int K>
 static int launch_const(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                         double tol, double* rho, int32_t* iters, unsigned int* queue, cudaStream_t st) {
     constexpr int D = 1 << (2 * N), d = 1 << N;
-    static ConstTables<N, K> ct;  // filled per launch from the plan's host copy (thread-compatible ABI)
+    ConstTables<N, K> ct;  // filled per launch from the plan's host copy; copied into the launch parameters
     for (int k = 0; k < K; ++k)
         for (int e = 0; e < D; ++e) {
             const double v = plan->Ar_host[(size_t)k * D + e];
@@ -687,7 +687,7 @@ int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, c
     if (!queue) return QPB_ERR_NOMEM;
     QPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), st));
     if (plan->n == 2 && plan->A_host && !getenv("QPB_NO_PAULI_KERNEL")) {
-        static PauliParams pp;
+        PauliParams pp;
         if (detect_pauli2(plan->A_host, plan->K, &pp)) {
             const size_t smem = sizeof(double) * 36 * kSmallThreads;
             int per_sm = 1;
