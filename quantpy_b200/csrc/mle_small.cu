@@ -480,25 +480,51 @@ struct PauliParams {
     int uniform;          // all used slots have the same guard (then every entry of epsp holds it)
 };
 
+// Tail merging.  The kernel runs ONE 256-thread CTA per SM: warps w and w+4 sit on the same scheduler.  While the
+// queue has work both are full; once it is empty each holds a few long-running samples and the two instruction
+// streams halve each other's FP64 issue rate.  The upper warp ("donor") therefore hands its remaining samples to
+// idle lanes of the lower warp ("receiver") through a shared-memory mailbox as soon as it has at most kDonateMax
+// of them, and exits.  A sample's iteration sequence is untouched, so results are bit-identical.
+// state word per pair: 0 open | 3 donor writing | 1 mail ready | 4 mail taken | 2 receiver gone
+constexpr int kPauliThreads = 256;
+constexpr int kDonateMax = 16;
+struct TailMail {
+    double h[kDonateMax][16];
+    long b[kDonateMax];
+    int it[kDonateMax];
+    int col[kDonateMax];
+};
+
 template <bool UNIFORM_GUARD>  // all used slots share one 1e-10/c: fold it into S_00 instead of 36 additions
-__global__ void __launch_bounds__(kSmallThreads)
+__global__ void __launch_bounds__(kPauliThreads, 1)
 k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* __restrict__ counts,
                  const double* __restrict__ rho0, int max_iter, double tol, double* __restrict__ rho,
-                 int32_t* __restrict__ iters, unsigned int* __restrict__ queue) {
+                 int32_t* __restrict__ iters, unsigned int* __restrict__ queue, int merge_tail) {
     constexpr int d = 4, D = 16;
     extern __shared__ __align__(16) double sm[];
-    double* fs = sm;  // [36][kSmallThreads]
-    const int tid = threadIdx.x, lane = tid & 31;
+    double* fs = sm;  // [36][kPauliThreads], column = owning thread at load time
+    __shared__ TailMail mail[4];
+    __shared__ int pair_state[4];
+    __shared__ int mail_count[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pair = warp & 3;
+    const bool donor = warp >= 4;
     const int K = pp.K;
-    for (int sl = 0; sl < 36; ++sl) fs[sl * kSmallThreads + tid] = 0.0;
+    for (int sl = 0; sl < 36; ++sl) fs[sl * kPauliThreads + tid] = 0.0;
+    if (tid < 4) pair_state[tid] = 0;
+    __syncthreads();
 
     double h[D];
     int it = 0;
+    int col = tid;      // fs column of the sample this lane owns
     long b = -1;
-    bool alive = true;
+    bool alive = true;  // false once the queue ran dry for this lane
+    bool can_merge = merge_tail != 0 && blockDim.x == kPauliThreads;
+    bool drained = false;  // warp-uniform: some lane has seen the queue empty (it never refills again)
     const double tol2 = tol * tol;
 
     while (true) {
+        // ---- refill lanes without work -------------------------------------------------------
         const bool want = alive && b < 0;
         const unsigned need = __ballot_sync(0xffffffffu, want);
         if (need) {
@@ -511,6 +537,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
                 if (nb < B) {
                     b = nb;
                     it = 0;
+                    col = tid;
                     // all K count loads are issued together (independent, predicated), then normalised
                     const int32_t* c = counts + b * K;
                     int cc[36];
@@ -522,7 +549,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
                     const double total = (double)tot;
 #pragma unroll
                     for (int k = 0; k < 36; ++k)
-                        if (k < K) fs[pp.slot_of_col[k] * kSmallThreads + tid] = (double)cc[k] / total;
+                        if (k < K) fs[pp.slot_of_col[k] * kPauliThreads + tid] = (double)cc[k] / total;
                     if (rho0) {
                         const double2* r0 = reinterpret_cast<const double2*>(rho0) + b * D;
 #pragma unroll
@@ -542,8 +569,75 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
                 }
             }
         }
-        if (!__any_sync(0xffffffffu, b >= 0)) break;
+        unsigned active = __ballot_sync(0xffffffffu, b >= 0);
+        if (!drained) drained = __any_sync(0xffffffffu, !alive);
 
+        // ---- tail merging (only once the queue is empty) ----------------------------------------
+        if (can_merge && drained) {
+            if (donor) {
+                const int nact = __popc(active);
+                if (nact > 0 && nact <= kDonateMax) {
+                    int old = 0;
+                    if (lane == 0) old = atomicCAS(&pair_state[pair], 0, 3);
+                    old = __shfl_sync(0xffffffffu, old, 0);
+                    if (old == 0) {
+                        if (b >= 0) {
+                            const int slot = __popc(active & ((1u << lane) - 1u));
+#pragma unroll
+                            for (int e = 0; e < D; ++e) mail[pair].h[slot][e] = h[e];
+                            mail[pair].b[slot] = b;
+                            mail[pair].it[slot] = it;
+                            mail[pair].col[slot] = col;
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            mail_count[pair] = nact;
+                            __threadfence_block();
+                            atomicExch(&pair_state[pair], 1);
+                        }
+                        b = -1;
+                        active = 0;
+                    } else {
+                        can_merge = false;  // the receiver has already left: finish alone
+                    }
+                }
+            } else {
+                int st = 0;
+                if (lane == 0) {
+                    st = *(volatile int*)&pair_state[pair];
+                    if (active == 0 && st != 1) {
+                        // about to leave: close the pair, or wait for a donor that is writing its mail
+                        const int old = atomicCAS(&pair_state[pair], 0, 2);
+                        st = old;
+                        while (st == 3) st = *(volatile int*)&pair_state[pair];
+                    }
+                }
+                st = __shfl_sync(0xffffffffu, st, 0);
+                if (st == 1) {
+                    __threadfence_block();
+                    const int cnt = mail_count[pair];
+                    const unsigned idle = ~active;
+                    if (__popc(idle) >= cnt) {
+                        const int rank = __popc(idle & ((1u << lane) - 1u));
+                        if (b < 0 && rank < cnt) {
+#pragma unroll
+                            for (int e = 0; e < D; ++e) h[e] = mail[pair].h[rank][e];
+                            b = mail[pair].b[rank];
+                            it = mail[pair].it[rank];
+                            col = mail[pair].col[rank];
+                        }
+                        __syncwarp();
+                        if (lane == 0) atomicExch(&pair_state[pair], 4);
+                        active = __ballot_sync(0xffffffffu, b >= 0);
+                    }
+                } else if (st != 0 && st != 3) {
+                    can_merge = false;  // pair closed (mail taken, or we closed it ourselves)
+                }
+            }
+        }
+        if (active == 0) break;
+
+        // ---- one R.rho.R iteration (lanes without a sample are predicated off) ---------------
         bool finished = false;
         if (b >= 0) {
             if (max_iter <= 0) {
@@ -569,7 +663,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
                         w[be] = UNIFORM_GUARD ? q : q + pp.epsp[al * 6 + be];
                     }
 #pragma unroll
-                    for (int be = 0; be < 6; ++be) w[be] = fs[(al * 6 + be) * kSmallThreads + tid] * fast_rcp(w[be]);
+                    for (int be = 0; be < 6; ++be) w[be] = fs[(al * 6 + be) * kPauliThreads + col] * fast_rcp(w[be]);
                     double u[4];
                     u[0] = ((w[0] + w[1]) + (w[2] + w[3])) + (w[4] + w[5]);
                     u[1] = w[0] - w[1];
@@ -689,16 +783,14 @@ int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, c
     if (plan->n == 2 && plan->A_host && !getenv("QPB_NO_PAULI_KERNEL")) {
         PauliParams pp;
         if (detect_pauli2(plan->A_host, plan->K, &pp)) {
-            const size_t smem = sizeof(double) * 36 * kSmallThreads;
-            int per_sm = 1;
+            const size_t smem = sizeof(double) * 36 * kPauliThreads;
             auto pk = pp.uniform ? k_mle_rrr_pauli2<true> : k_mle_rrr_pauli2<false>;
-            QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk, kSmallThreads, smem));
-            if (per_sm < 1) per_sm = 1;
-            if (per_sm > kMaxBlocksPerSm) per_sm = kMaxBlocksPerSm;
-            long blocks = (long)num_sms() * per_sm;
-            const long need = ((long)B + kSmallThreads - 1) / kSmallThreads;
+            QPB_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            long blocks = num_sms();  // one 8-warp CTA per SM: warps w and w+4 share a scheduler (tail merging)
+            const long need = ((long)B + kPauliThreads - 1) / kPauliThreads;
             if (blocks > need) blocks = need;
-            pk<<<(int)blocks, kSmallThreads, smem, st>>>(pp, B, counts, rho0, max_iter, tol, rho, iters, queue);
+            const int merge = getenv("QPB_NO_TAIL_MERGE") ? 0 : 1;
+            pk<<<(int)blocks, kPauliThreads, smem, st>>>(pp, B, counts, rho0, max_iter, tol, rho, iters, queue, merge);
             QPB_LAUNCHED("k_mle_rrr_pauli2");
             return QPB_OK;
         }
