@@ -60,11 +60,40 @@ def all_gather_concat(local, n_total):
     return torch.cat(pieces)
 
 
-def quantile_function(dist_values, presorted=False):
-    """Sorted distances -> interp1d(linspace(0, 1, N), dist) as quantpy/tomography/interval.py:610-612."""
-    from scipy.interpolate import interp1d
+class QuantileFunction:
+    """Linear interpolant of the sorted bootstrap distances on the grid linspace(0, 1, N) -- the object the
+    reference builds with scipy.interpolate.interp1d(conf_levels, dist) (quantpy/tomography/interval.py:610-612).
+    Same call semantics (vectorised, ValueError outside [0, 1]) and the same `.x` / `.y` attributes, but
+    nothing of size N is built until it is asked for, which keeps the end-to-end bootstrap call short."""
 
+    def __init__(self, sorted_values):
+        self.y = np.asarray(sorted_values, dtype=np.float64)
+        self._x = None
+
+    @property
+    def x(self):
+        if self._x is None:
+            self._x = np.linspace(0, 1, len(self.y))
+        return self._x
+
+    def __call__(self, levels):
+        levels = np.asarray(levels, dtype=np.float64)
+        if np.any(levels < 0):
+            raise ValueError("A value in x_new is below the interpolation range.")
+        if np.any(levels > 1):
+            raise ValueError("A value in x_new is above the interpolation range.")
+        n = len(self.y)
+        if n == 1:
+            return np.full(levels.shape, self.y[0])
+        pos = levels * (n - 1)
+        lo = np.minimum(np.floor(pos).astype(np.int64), n - 2)
+        frac = pos - lo
+        return self.y[lo] + (self.y[lo + 1] - self.y[lo]) * frac
+
+
+def quantile_function(dist_values, presorted=False):
+    """Sorted distances -> interpolant of (linspace(0, 1, N), dist) as quantpy/tomography/interval.py:610-612."""
     ordered = np.asarray(dist_values, dtype=np.float64)
     if not presorted:
         ordered = np.sort(ordered)
-    return interp1d(np.linspace(0, 1, len(ordered)), ordered, assume_sorted=True)
+    return QuantileFunction(ordered)

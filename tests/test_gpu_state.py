@@ -376,3 +376,18 @@ def test_state_tomograph_api(qp):
         tmg.experiment([10, 20], "proj-set")
     with pytest.raises(ValueError):
         qp.StateTomograph(qp.Qobj(rho), dst="nope")
+
+
+def test_tail_merging_is_bit_identical(qp, monkeypatch):
+    """The structured kernel hands a warp's last samples to its partner warp once the queue is empty; every
+    sample still runs its own iteration sequence, so the output must not change by a single bit."""
+    rho = haar(2, 5)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(0)
+    tmg.experiment(10000, "proj")
+    counts = tmg.sample_counts(60000, 10000, "proj", seed=3)
+    a, ia = tmg.point_estimate_batch(counts, "mle", max_iter=400, tol=1e-6, return_iters=True)
+    monkeypatch.setenv("QPB_NO_TAIL_MERGE", "1")
+    b, ib = tmg.point_estimate_batch(counts, "mle", max_iter=400, tol=1e-6, return_iters=True)
+    assert np.array_equal(ia, ib) and np.array_equal(a, b)
+    assert ia.max() == 400 and ia.min() < 50
