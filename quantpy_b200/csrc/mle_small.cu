@@ -680,18 +680,17 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
                 pauli2::all_r(g, R);
                 double hn[D];
                 rrr_apply<d>(R, h, hn);
-                double tr = 0.0;
-#pragma unroll
-                for (int a = 0; a < d; ++a) tr += hn[a * d + a];
+                const double tr = (hn[0] + hn[5]) + (hn[10] + hn[15]);
                 const double inv = fast_rcp(tr);
-                double del = 0.0;
+                double dl[4] = {0.0, 0.0, 0.0, 0.0};  // four partial sums: no 16-deep dependent FMA chain
 #pragma unroll
                 for (int e = 0; e < D; ++e) {
                     const double v = hn[e] * inv;
                     const double df = v - h[e];
-                    del = fma((e / d == e % d) ? df : 2.0 * df, df, del);
+                    dl[e & 3] = fma((e / d == e % d) ? df : 2.0 * df, df, dl[e & 3]);
                     h[e] = v;
                 }
+                const double del = (dl[0] + dl[1]) + (dl[2] + dl[3]);
                 ++it;
                 finished = (del < tol2) || (it >= max_iter);
             }
