@@ -58,7 +58,8 @@ class ConfidenceInterval(ABC):
     def _finish(self, local_dist, n_points):
         """All-gather the per-rank distances, keep them (sorted) and build the quantile function."""
         full = parallel.all_gather_concat(local_dist, n_points)
-        self.dist = full.sort().values.cpu().numpy()  # sort on the device, one D2H copy of N doubles
+        ordered = full.sort().values  # sort on the device, then one D2H copy of N doubles through pinned memory
+        self.dist = parallel.to_host_pinned(ordered)
         self.cl_to_dist = parallel.quantile_function(self.dist, presorted=True)
 
 
