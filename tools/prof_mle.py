@@ -20,3 +20,12 @@ for rep in range(2):
     out = plan.bootstrap(probs, B, 1 + rep, 0, rho, method="mle", max_iter=max_iter, tol=tol)
 torch.cuda.synchronize()
 print("mean iters", out["iters"].double().mean().item(), "median dist", out["dist"].median().item())
+if len(sys.argv) > 4 and sys.argv[4] == "time":   # MLE kernel(s) alone, CUDA events
+    cnt = plan.sample(probs, B, 1, 0)
+    start = plan.lin(cnt, True)
+    best = 1e9
+    for rep in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); r = plan.mle(cnt, start, max_iter, tol); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print("mle ms %.3f" % best)

@@ -15,4 +15,11 @@ probs = plan.probabilities(qp.Qobj(rho).bloch)[0]
 for rep in range(3):
     c = plan.sample(probs, B, 1 + rep, 0)
 torch.cuda.synchronize()
-print("mean", c.double().mean().item())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+reps = 20
+e0.record()
+for rep in range(reps):
+    c = plan.sample(probs, B, 10 + rep, 0)
+e1.record(); torch.cuda.synchronize()
+print("n", n, "B", B, "sampler", os.environ.get("QPB_SAMPLER", "auto"), "flat" if os.environ.get("QPB_FLAT_BINOMIAL") else "grouped",
+      "ms/launch %.3f" % (e0.elapsed_time(e1) / reps), "mean", c.double().mean().item())
