@@ -186,6 +186,39 @@ def mle_bfgs(counts, povm, n_meas=None, init="lin", max_iter=100, tol=1e-3):
     return m / np.trace(m)
 
 
+def mle_slsqp(counts, povm, n_meas=None, init="lin", max_iter=100, tol=1e-3):
+    """The reference's 'mle-constr': the same Cholesky-parametrised likelihood as `mle_bfgs`, minimised by
+    SciPy SLSQP under the equality Tr(L L^dagger) = 1.  state.py:231-254, 262-265."""
+    povm = np.asarray(povm, dtype=float)
+    counts = np.asarray(counts)
+    if n_meas is None:
+        n_meas = counts.sum(-1)
+    n = n_qubits_from_D(povm.shape[-1])
+    if init == "mixed":
+        start = np.eye(2**n, dtype=np.complex128) / 2**n
+    elif init == "lin":
+        start = lin_estimate(counts, povm, n_meas, physical=True)
+    else:
+        raise ValueError("Invalid value for argument `init`")
+    A = weighted_povm(povm, n_meas)
+    f = counts.reshape(-1) / np.sum(n_meas)
+    S = pauli_basis(n)
+    d = 2**n
+
+    def nll(x):
+        m = _chol_unpack(x)
+        m = m / np.trace(m)
+        bloch = np.real(np.einsum("iab,ab->i", S, np.conj(m))) / d
+        return -np.sum(f * np.log(A @ bloch * d + LOG_GUARD))
+
+    # the reference returns the complex trace; SLSQP keeps its real part (ComplexWarning there)
+    unit_trace = [{"type": "eq", "fun": lambda x: np.real(np.trace(_chol_unpack(x))) - 1}]
+    res = minimize(nll, _chol_pack(start), constraints=unit_trace, method="SLSQP", tol=tol,
+                   options={"maxiter": max_iter})
+    m = _chol_unpack(res.x)
+    return m / np.trace(m)
+
+
 # ----------------------------------------------------------------------------- R.rho.R MLE (kernel specification)
 
 def povm_operators(A):

@@ -128,17 +128,16 @@ class BootstrapStateInterval(ConfidenceInterval):
             else:
                 self.state = self.tmg.point_estimate(method=self.method, physical=self.physical, init=self.init,
                                                      tol=self.tol, max_iter=self.max_iter)
-        if self.method == "mle-constr":
-            raise NotImplementedError("'mle-constr' (SLSQP) is outside the B200 hot path; use 'mle'")
-        if self.method not in ("lin", "mle"):
+        if self.method not in ("lin", "mle", "mle-constr"):
             raise ValueError("Invalid value for argument `method`")
+        method = "mle" if self.method == "mle-constr" else self.method  # same maximiser, same kernel
         rank, size = parallel.world()
         lo, hi = parallel.shard_bounds(self.n_points, rank, size)
         seed = parallel.broadcast_seed(engine.next_seed() if seed is None else int(seed))
         plan = engine.state_plan(self.tmg.povm_matrix, self.tmg.n_measurements)
         probs = plan.probabilities(self.state.bloch)[0]
         kind = dst_kind(self.tmg.dst)
-        out = plan.bootstrap(probs, hi - lo, seed, lo, self.state.matrix, self.method, self.physical, self.init,
+        out = plan.bootstrap(probs, hi - lo, seed, lo, self.state.matrix, method, self.physical, self.init,
                              self.max_iter, self.tol, kind or "hs", keep=kind is None)
         if kind is None:  # user-supplied measure: evaluate it on the reconstructed batch
             from ..qobj import Qobj

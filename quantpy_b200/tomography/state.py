@@ -10,7 +10,8 @@ reference class.  The per-sample arithmetic runs in CUDA kernels through quantpy
 `method='mle'` is the iterative R.rho.R maximum-likelihood update asked for by the task statement,
 not the reference's SciPy BFGS over a Cholesky factor: `max_iter` caps the number of R.rho.R
 iterations and `tol` is the Frobenius norm of the last step (see DESIGN.md "MLE semantics").
-`'mle-constr'` is outside the hot path and raises NotImplementedError.
+`'mle-constr'` (the reference's SLSQP variant of the same likelihood under Tr rho = 1, state.py:231-254) has the
+same maximiser over physical states; it is accepted and runs the same R.rho.R kernel.
 
 Batched extensions used by the bootstrap: `sample_counts`, `point_estimate_batch`.
 """
@@ -108,8 +109,8 @@ class StateTomograph:
         """Reconstruct a batch of count tables [B, P, O] measured with this tomograph's POVM and shots.
         Returns complex matrices [B, d, d] (and the R.rho.R iteration counts when asked)."""
         torch = nt.torch_cuda()
-        if method == "mle-constr":
-            raise NotImplementedError("'mle-constr' (SLSQP) is outside the B200 hot path; use 'mle'")
+        if method == "mle-constr":  # same likelihood, same feasible set: R.rho.R keeps Tr rho = 1 and rho >= 0
+            method = "mle"
         if method not in ("lin", "mle"):
             raise ValueError("Invalid value for argument `method`")
         plan = self._plan()
@@ -124,7 +125,7 @@ class StateTomograph:
     def point_estimate(self, method="lin", physical=True, init="lin", max_iter=100, tol=1e-3):
         """Reconstruct the density matrix from `results` (state.py:143-189).
 
-        method : 'lin' (linear inversion) | 'mle' (iterative maximum likelihood)
+        method : 'lin' (linear inversion) | 'mle' | 'mle-constr' (both: iterative maximum likelihood)
         physical : project the 'lin' estimate onto physical states (clip eigenvalues at 1e-15, renormalise)
         init : start of the MLE iteration, 'lin' (physical linear-inversion estimate) | 'mixed'
         max_iter, tol : iteration cap and step-norm stopping threshold of the MLE iteration

@@ -318,8 +318,27 @@ def test_mle_edge_cases(qp):
         tmg.point_estimate("nope")
     with pytest.raises(ValueError):
         tmg.point_estimate("mle", init="nope")
-    with pytest.raises(NotImplementedError):
-        tmg.point_estimate("mle-constr")
+
+
+@pytest.mark.parametrize("case", ["state_c1", "state_c2_set"])
+def test_mle_constr_runs_the_same_kernel_and_dominates_reference(qp, golden, case):
+    """'mle-constr' (reference: SLSQP under Tr rho = 1, state.py:231-254) maximises the same likelihood over the
+    same set; here it is the R.rho.R kernel.  Tier-2 parity as for 'mle': at least as likely as the reference's
+    answer, and equal to it within the reference optimiser's own noise floor."""
+    g, ref = golden(case), golden("mle_constr")
+    tmg = qp.StateTomograph(qp.Qobj(g["rho_true"]))
+    tmg.povm_matrix = g["povm_matrix"]
+    for i, c in enumerate(g["counts"][:4]):
+        tmg.results = c
+        tmg.n_measurements = g["n_meas"]
+        a = tmg.point_estimate("mle-constr", tol=1e-12, max_iter=20000).matrix
+        b = tmg.point_estimate("mle", tol=1e-12, max_iter=20000).matrix
+        assert np.array_equal(a, b)
+        ours = ostate.neg_log_likelihood(a, c, g["povm_matrix"], g["n_meas"])
+        for key in ("_default", "_tight"):
+            theirs = ostate.neg_log_likelihood(ref[case + key][i], c, g["povm_matrix"], g["n_meas"])
+            assert ours <= theirs + 1e-9
+        assert np.linalg.norm(a - ref[case + "_tight"][i]) < 2e-6
 
 
 # ----------------------------------------------------------------------------- distances

@@ -88,6 +88,23 @@ def test_mle_bfgs_matches_reference(golden, case):
         assert fro(got, g["mle_default"][i]) < 1e-5
 
 
+@pytest.mark.parametrize("case", ["state_c1", "state_c2_set"])
+def test_mle_slsqp_matches_reference_and_rrr_dominates_it(golden, case):
+    """'mle-constr' (state.py:231-254): the restatement reproduces the reference's SLSQP answers, and R.rho.R
+    reaches a likelihood at least as high and the same state up to SLSQP's noise floor."""
+    g, ref = golden(case), golden("mle_constr")
+    povm, n_meas = g["povm_matrix"], g["n_meas"]
+    rrr = ostate.mle_rrr(g["counts"][:4], povm, n_meas, max_iter=20000, tol=1e-13)
+    for i, c in enumerate(g["counts"][:4]):
+        assert fro(ostate.mle_slsqp(c, povm, n_meas), ref[case + "_default"][i]) < 1e-9
+        if i < 2:
+            assert fro(ostate.mle_slsqp(c, povm, n_meas, tol=1e-12, max_iter=1000), ref[case + "_tight"][i]) < 5e-6
+        ours = ostate.neg_log_likelihood(rrr[i], c, povm, n_meas)
+        for key in ("_default", "_tight"):
+            assert ours <= ostate.neg_log_likelihood(ref[case + key][i], c, povm, n_meas) + 1e-9
+        assert fro(rrr[i], ref[case + "_tight"][i]) < 2e-6
+
+
 @pytest.mark.parametrize("case", ["state_c1", "state_c1_pure", "state_c2", "state_c2_set",
                                   "state_c2_rank1", "state_c2_sic"])
 def test_rrr_is_at_least_as_likely_as_reference_mle(golden, case):

@@ -215,7 +215,7 @@ def main():
         print(f"{name}: {os.path.getsize(path)} bytes")
 
 
-if __name__ == "__main__" and "--polytopes" not in sys.argv and "--moments" not in sys.argv:
+if __name__ == "__main__" and not {"--polytopes", "--moments", "--mle-constr"} & set(sys.argv):
     main()
 
 
@@ -303,3 +303,30 @@ if __name__ == "__main__" and "--moments" in sys.argv:
     path = os.path.join(OUT, "moments.npz")
     np.savez_compressed(path, **arrays)
     print(f"moments: {os.path.getsize(path)} bytes")
+
+
+def mle_constr_cases(qp):
+    """Reference 'mle-constr' (SLSQP with the unit-trace equality, state.py:231-254) on the counts already stored
+    in state_c1 / state_c2_set, at the default and at a tight tolerance."""
+    out = {}
+    for tag in ("state_c1", "state_c2_set"):
+        g = np.load(os.path.join(OUT, tag + ".npz"))
+        tmg = qp.StateTomograph(qp.Qobj(g["rho_true"]))
+        tmg.povm_matrix = g["povm_matrix"]
+        default, tight = [], []
+        for c in g["counts"][:4]:
+            tmg.results = c
+            tmg.n_measurements = g["n_meas"]
+            default.append(tmg.point_estimate("mle-constr").matrix)
+            tight.append(tmg.point_estimate("mle-constr", tol=1e-12, max_iter=1000).matrix)
+        out[tag + "_default"] = np.array(default)
+        out[tag + "_tight"] = np.array(tight)
+    return out
+
+
+if __name__ == "__main__" and "--mle-constr" in sys.argv:
+    warnings.filterwarnings("ignore")
+    arrays = mle_constr_cases(load_reference())
+    path = os.path.join(OUT, "mle_constr.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"mle_constr: {os.path.getsize(path)} bytes")
