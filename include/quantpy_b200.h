@@ -154,6 +154,22 @@ QPB_API int qpb_polytope_confidence(int B, int M, int O, const double* freq, con
 QPB_API int qpb_l2_moments(int B, int P, int O, const double* weights, const double* freq, double n_trials,
                    double* mean_out, double* var_out, void* stream);
 
+/* ---- Metropolis-Hastings likelihood sampling (fourth "next" row) ---------
+ * MHMC.sample with normalized_update and a symmetric standard-normal jump (quantpy/mhmc.py:48-119) on the target
+ * exp(-StateTomograph._nll(x)) (state.py:217-229), as MHMCStateInterval.setup runs it (interval.py:737-759).
+ * C independent chains, one warp each; chain c starts at the packed Cholesky vector x_init[c] [D]
+ * (routines.py:84-91), makes burn_steps steps, then n_samples*thinning steps of which every thinning-th state
+ * (i % thinning == 0) is returned as L L^dagger in samples [C, n_samples, d, d] complex128.
+ * counts [K] (counts_batched = 0) or [C, K]; accepted [C] = accepted proposals of the sampling phase (may be NULL);
+ * x_final [C, D] = last state, for warm starts (may be NULL).
+ * Noise: deltas [C, burn_steps + n_samples*thinning, D] and uniforms [C, burn_steps + n_samples*thinning] from the
+ * caller (both or neither); when NULL it is generated in the kernel from Philox4x32-10 keyed by seed with counter
+ * (chain_offset + c, step).                                                                              */
+QPB_API int qpb_mhmc_state(const qpb_state_plan* plan, int C, int n_samples, int thinning, int burn_steps, double step,
+                   const int32_t* counts, int counts_batched, const double* x_init, const double* deltas,
+                   const double* uniforms, uint64_t seed, uint64_t chain_offset, double* samples, int32_t* accepted,
+                   double* x_final, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,6 +170,46 @@ class StatePlan:
         return bufs
 
 
+def cholesky_vector(matrix):
+    """Packed Cholesky parametrisation of a positive-definite matrix (quantpy/routines.py:84-91): the diagonal of
+    the lower factor, then the real and the imaginary parts of its strict lower triangle (np.tril_indices order).
+    Raises numpy.linalg.LinAlgError for a singular matrix, as the reference's la.cholesky does."""
+    low = np.linalg.cholesky(np.asarray(matrix, dtype=np.complex128))
+    strict = low[np.tril_indices(low.shape[0], -1)]
+    return np.concatenate([np.real(np.diag(low)), strict.real, strict.imag])
+
+
+def mhmc_chains(plan, counts, x_init, n_samples, step, burn_steps, thinning, deltas=None, uniforms=None, seed=0,
+                chain_offset=0):
+    """Metropolis-Hastings chains on the likelihood of `counts` (quantpy/mhmc.py:48-119 with normalized_update).
+    x_init [C, D] packed Cholesky start vectors; counts [K] (shared) or [C, K].  deltas [C, T, D] / uniforms [C, T]
+    (T = burn_steps + n_samples*thinning) replay a given noise stream; without them the kernel draws Philox noise.
+    Returns dict(samples [C, n_samples, d, d, 2] device, accepted [C] device, x_final [C, D] device)."""
+    torch = nt.torch_cuda()
+    lib = nt.load_library()
+    x0 = nt.to_device(np.asarray(x_init, dtype=np.float64).reshape(-1, plan.D), torch.float64)
+    C = x0.shape[0]
+    if torch.is_tensor(counts):
+        cnt = counts.to(torch.int32).contiguous()
+    else:
+        cnt = nt.to_device(np.asarray(counts).reshape(-1, plan.K), torch.int32)
+    batched = int(cnt.numel() == C * plan.K and C > 1)
+    if not batched and cnt.numel() != plan.K:
+        raise ValueError("counts must hold one table or one table per chain")
+    total = int(burn_steps) + int(n_samples) * int(thinning)
+    dl = ul = None
+    if deltas is not None:
+        dl = nt.to_device(np.asarray(deltas, dtype=np.float64).reshape(C, total, plan.D), torch.float64)
+        ul = nt.to_device(np.asarray(uniforms, dtype=np.float64).reshape(C, total), torch.float64)
+    samples = torch.empty((C, n_samples, plan.d, plan.d, 2), dtype=torch.float64, device="cuda")
+    accepted = torch.zeros((C,), dtype=torch.int32, device="cuda")
+    x_final = torch.empty((C, plan.D), dtype=torch.float64, device="cuda")
+    nt.check(lib.qpb_mhmc_state(plan.handle, C, int(n_samples), int(thinning), int(burn_steps), float(step), nt.ptr(cnt),
+                                batched, nt.ptr(x0), nt.ptr(dl), nt.ptr(ul), int(seed), int(chain_offset),
+                                nt.ptr(samples), nt.ptr(accepted), nt.ptr(x_final), nt.stream_ptr()))
+    return {"samples": samples, "accepted": accepted, "x_final": x_final}
+
+
 def distance(rho, ref_matrix, dst="hs"):
     """dst(rho[b], ref) for a device batch rho [B, s, s, 2] -> device [B] (k8)."""
     torch = nt.torch_cuda()

@@ -157,6 +157,59 @@ class BootstrapStateInterval(ConfidenceInterval):
         return self._iters_dev.cpu().numpy()
 
 
+class MHMCStateInterval(ConfidenceInterval):
+    def __init__(self, tmg, n_points=1000, step=0.01, burn_steps=1000, thinning=1, warm_start=False,
+                 use_new_estimate=False, state=None, verbose=False):
+        """Metropolis-Hastings samples from the likelihood, distances to the point estimate
+        (quantpy/tomography/interval.py:689-759, chain: quantpy/mhmc.py:48-119).
+
+        The chain is the reference's: packed Cholesky vector on the unit sphere, proposal
+        (x + step*delta)/|x + step*delta| with delta ~ N(0, I), target exp(-tmg._nll(x)).  Its noise is drawn on
+        the host from the legacy np.random stream in the reference's order (burn-in deltas, burn-in uniforms,
+        sampling deltas, sampling uniforms), so `np.random.seed(s)` reproduces the reference's chain; the
+        steps themselves run in one CUDA kernel (qpb_mhmc_state).  `verbose` is accepted and ignored."""
+        super().__init__(tmg, **_pop_hidden_keys(locals()))
+
+    def setup(self):
+        if self.mode == Mode.CHANNEL:
+            raise NotImplementedError("This interval works only for state tomography")
+        if not self.use_new_estimate:
+            self.state = self.tmg.reconstructed_state
+        elif self.state is None:
+            self.state = self.tmg.point_estimate(method="mle", physical=True)
+        plan = engine.state_plan(self.tmg.povm_matrix, self.tmg.n_measurements)
+        dim = plan.D
+        warm = self.warm_start and hasattr(self, "_x_t")
+        x_init = self._x_t if warm else engine.cholesky_vector(self.state.matrix)
+        burn = 0 if warm else int(self.burn_steps)
+        total = int(self.n_points) * int(self.thinning)
+        # mhmc.py:70-71, 89-90: jump_distr.rvs (SciPy's frozen N(0, I) calls multivariate_normal of the global
+        # legacy stream) and np.random.rand, burn-in first
+        mean, cov = np.zeros(dim), np.eye(dim)
+        parts_d, parts_u = [], []
+        for size in ([burn] if burn else []) + [total]:
+            parts_d.append(np.random.multivariate_normal(mean, cov, size).reshape(size, dim))
+            parts_u.append(np.random.rand(size))
+        out = engine.mhmc_chains(plan, self.tmg.results, x_init[None], self.n_points, self.step, burn, self.thinning,
+                                 np.concatenate(parts_d)[None], np.concatenate(parts_u)[None])
+        self._x_t = out["x_final"][0].cpu().numpy()
+        self.acceptance_rate = float(out["accepted"][0].item()) / total
+        kind = dst_kind(self.tmg.dst)
+        samples = out["samples"][0]
+        if kind is None:
+            from ..qobj import Qobj
+
+            mats = nt.complex_to_host(samples)
+            dist = np.sort([float(self.tmg.dst(Qobj(m), self.state)) for m in mats])
+            self.dist = dist
+            self.cl_to_dist = parallel.quantile_function(dist, presorted=True)
+            return
+        local = engine.distance(samples, self.state.matrix, kind)
+        ordered = local.sort().values
+        self.dist = parallel.to_host_pinned(ordered)
+        self.cl_to_dist = parallel.quantile_function(self.dist, presorted=True)
+
+
 class BootstrapProcessInterval(ConfidenceInterval):
     def __init__(self, tmg, n_points=1000, method="lifp", cptp=True, tol=1e-10, channel=None,
                  states_est_method="lin", states_physical=True, states_init="lin"):
@@ -230,5 +283,4 @@ SugiyamaInterval = _out_of_scope("SugiyamaInterval")
 PolytopeStateInterval = _out_of_scope("PolytopeStateInterval")
 PolytopeProcessInterval = _out_of_scope("PolytopeProcessInterval")
 HolderInterval = _out_of_scope("HolderInterval")
-MHMCStateInterval = _out_of_scope("MHMCStateInterval")
 MHMCProcessInterval = _out_of_scope("MHMCProcessInterval")

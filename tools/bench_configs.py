@@ -49,10 +49,29 @@ def process_case(name, n, B):
     ms, (d, iters) = timed(run, reps=2)
     print(f"{name}: process n={n} S={4**n} 'sic' inputs, proj-set, B={B} lifp+CPTP: {ms:9.3f} ms  {B/ms:9.2f} krec/s  mean CPTP iters={iters.double().mean().item():.1f}", flush=True)
 
+def mhmc_case(n, povm, n_points, burn, chains):
+    """MHMCStateInterval's chain (one warp per chain): the reference's single chain, and a batch with Philox noise."""
+    rho = haar(n, 0)
+    pm = qp.generate_measurement_matrix(povm, n)
+    plan = engine.state_plan(pm, np.ones(pm.shape[0]) * 10000)
+    probs = plan.probabilities(qp.Qobj(rho).bloch)[0].contiguous()
+    counts = plan.sample(probs, 1, 1, 0)[0]
+    x0 = engine.cholesky_vector(rho)
+    rng = np.random.default_rng(1)
+    total = burn + n_points
+    dl, ul = rng.normal(size=(1, total, plan.D)), rng.random((1, total))
+    t1, _ = timed(lambda: engine.mhmc_chains(plan, counts, x0[None], n_points, 0.01, burn, 1, dl, ul))
+    tc, out = timed(lambda: engine.mhmc_chains(plan, counts, np.tile(x0, (chains, 1)), n_points, 0.01, burn, 1, seed=5))
+    print(f"MHMC n={n} {povm}: 1 chain x {total} steps (host noise incl. H2D) {t1:.3f} ms = {t1 * 1e3 / total:.2f} us/step; "
+          f"{chains} chains {tc:.3f} ms = {chains * total / tc / 1e3:.2f} Msteps/s, acceptance "
+          f"{out['accepted'].double().mean().item() / n_points:.3f}", flush=True)
+
+
 which = sys.argv[1:] or ["c1", "c2", "c3", "c4", "c5"]
 if "c1" in which: state_case("C1", 1, "proj-set", 1000, "mle", 1e-6, 1000); state_case("C1b", 1, "proj-set", 100000, "mle", 1e-6, 1000)
 if "c2" in which: state_case("C2", 2, "proj", 100000, "mle", 1e-6, 1000); state_case("C2-lin", 2, "proj", 100000, "lin", 0, 0)
 if "c3" in which: state_case("C3", 3, "proj", 100000, "lin", 0, 0)
 if "c3m" in which: state_case("C3-mle", 3, "proj", 2000, "mle", 1e-6, 1000)
 if "c4" in which: state_case("C4-lin", 4, "proj", 10000, "lin", 0, 0); state_case("C4", 4, "proj", int(os.environ.get("C4B", "256")), "mle", 1e-6, 200)
+if "mhmc" in which: mhmc_case(1, "proj-set", 1000, 1000, 4096); mhmc_case(2, "proj", 1000, 1000, 4096)
 if "c5" in which: process_case("C5-1q", 1, 20000); process_case("C5-2q", 2, 500)

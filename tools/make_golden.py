@@ -215,7 +215,7 @@ def main():
         print(f"{name}: {os.path.getsize(path)} bytes")
 
 
-if __name__ == "__main__" and not {"--polytopes", "--moments", "--mle-constr"} & set(sys.argv):
+if __name__ == "__main__" and not {"--polytopes", "--moments", "--mle-constr", "--mhmc"} & set(sys.argv):
     main()
 
 
@@ -330,3 +330,38 @@ if __name__ == "__main__" and "--mle-constr" in sys.argv:
     path = os.path.join(OUT, "mle_constr.npz")
     np.savez_compressed(path, **arrays)
     print(f"mle_constr: {os.path.getsize(path)} bytes")
+
+
+def mhmc_cases(qp):
+    """MHMCStateInterval (interval.py:689-759) with seeded legacy-RNG streams: inputs, the chain's samples and the
+    sorted distances."""
+    out = {}
+    for tag, n, povm, shots, seed, kw in (
+        ("q1", 1, "proj-set", 1000, 71, dict(n_points=120, step=0.05, burn_steps=60, thinning=2)),
+        ("q2", 2, "proj", 10000, 72, dict(n_points=60, step=0.01, burn_steps=40, thinning=1)),
+    ):
+        rho = haar_mixed(n, np.random.default_rng(seed))
+        tmg = qp.StateTomograph(qp.Qobj(rho))
+        np.random.seed(seed)
+        tmg.experiment(shots, povm)
+        centre = tmg.point_estimate("mle")
+        itv = qp.MHMCStateInterval(tmg, **kw)
+        np.random.seed(seed + 1)
+        itv.setup()
+        out[tag + "_counts"] = tmg.results.copy()
+        out[tag + "_povm"] = tmg.povm_matrix
+        out[tag + "_n_meas"] = np.asarray(tmg.n_measurements, float)
+        out[tag + "_centre"] = centre.matrix
+        out[tag + "_seed"] = seed + 1
+        out[tag + "_params"] = np.array([kw["n_points"], kw["step"], kw["burn_steps"], kw["thinning"]], float)
+        out[tag + "_sorted_dist"] = itv.cl_to_dist.y
+        out[tag + "_x_final"] = itv.chain.x_t
+    return out
+
+
+if __name__ == "__main__" and "--mhmc" in sys.argv:
+    warnings.filterwarnings("ignore")
+    arrays = mhmc_cases(load_reference())
+    path = os.path.join(OUT, "mhmc.npz")
+    np.savez_compressed(path, **arrays)
+    print(f"mhmc: {os.path.getsize(path)} bytes")
