@@ -16,9 +16,10 @@ collective; the e2e leg adds the one all-gather of distances).
            between steps, max over ranks.
 `e2e`      the same metric through the public API (BootstrapStateInterval.setup) with host inputs
            and host outputs inside the timed region.
-`roofline` for the dominant kernel (k_mle_rrr_small): algorithmic FP64 flops / CUDA-event duration of
-           that kernel alone, against the FP64 FMA peak measured live by qpb_fp64_fma_probe
-           (MEASURED_PEAKS.json has no FP64 figure); HBM GB/s is reported beside it.
+`roofline` for the dominant kernel (the R.rho.R MLE kernel qpb_mle_variant reports, k_mle_rrr_pauli2 at this
+           config): executed FP64 flops / CUDA-event duration of that kernel alone, against the FP64 FMA peak
+           measured live by qpb_fp64_fma_probe (MEASURED_PEAKS.json has no FP64 figure); the dense-equivalent
+           rate of SURVEY 8d (`survey_8d`) and the HBM GB/s are reported beside it.
 `cpu_baseline`  the oracle's port of the reference algorithm (SciPy BFGS 'mle') timed on one host core.
 
 --impl reference times that CPU port on all host cores and prints the same JSON shape.
@@ -42,10 +43,12 @@ METRIC = "MLE bootstrap reconstructions/sec (2-qubit Pauli POVM)"
 UNIT = "reconstructions/s"
 
 
-def haar_mixed(n, seed):
+def haar_mixed(n, seed, rank=0):
+    """rho = G G^dagger / Tr, G complex Ginibre d x rank (rank 0 = full rank)."""
     rng = np.random.default_rng(seed)
     d = 2**n
-    g = rng.normal(size=(d, d)) + 1j * rng.normal(size=(d, d))
+    k = rank or d
+    g = rng.normal(size=(d, k)) + 1j * rng.normal(size=(d, k))
     rho = g @ g.conj().T
     return rho / np.trace(rho)
 
@@ -66,12 +69,13 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--state-seed", type=int, default=0)
+    ap.add_argument("--state-rank", type=int, default=0, help="rank of the synthetic state (0 = full rank)")
     return ap.parse_args()
 
 
 def workload_config(args, world):
     return {
-        "workload": f"BASELINE configs[1]: {args.n_qubits}-qubit Haar-random state (seed {args.state_seed}), "
+        "workload": f"BASELINE configs[1]: {args.n_qubits}-qubit Haar-random state (seed {args.state_seed}{", rank %d" % args.state_rank if args.state_rank else ""}), "
                     f"{6**args.n_qubits if args.povm == 'proj' else '?'}-outcome Pauli '{args.povm}' POVM, "
                     f"{args.shots} shots, {args.resamples} {args.method.upper()} bootstrap resamples per GPU per step",
         "n_qubits": args.n_qubits, "povm": args.povm, "shots": args.shots,
@@ -187,7 +191,7 @@ def run_reference(args, rank, world):
     from oracle import state as ostate
 
     warnings.filterwarnings("ignore")
-    centre = haar_mixed(args.n_qubits, args.state_seed)
+    centre = haar_mixed(args.n_qubits, args.state_seed, args.state_rank)
     povm = ostate.measurement_matrix(args.povm, args.n_qubits)
     n_meas = np.ones(povm.shape[0]) * args.shots
     cores = os.cpu_count() or 1
@@ -261,7 +265,7 @@ def run_ours(args, rank, local_rank, world):
         return float(t.item())
 
     n, B = args.n_qubits, args.resamples
-    centre = haar_mixed(n, args.state_seed)
+    centre = haar_mixed(n, args.state_seed, args.state_rank)
     state = qp.Qobj(centre)
     povm = qp.generate_measurement_matrix(args.povm, n)
     n_meas = np.ones(povm.shape[0]) * args.shots
