@@ -249,7 +249,19 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries exactly one JSON line: NCCL prints its banner ("NCCL version ...") to fd 1 when the
+        # communicator comes up, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     lib = nt.load_library()
 
     def barrier():
@@ -308,8 +320,11 @@ def run_ours(args, rank, local_rank, world):
     tmg.results = np.zeros(povm.shape[:2], dtype=np.int64)  # bookkeeping only; the centre is given explicitly
     tmg.n_measurements = n_meas
     e2e_steps = max(2, min(args.steps, 5))
-    h2d = probs.numel() * 8 + state.bloch.size * 8 + ref.numel() * 8
-    d2h = (B * 8 + B * 4)
+    from quantpy_b200 import parallel as qpar
+
+    h2d = probs.numel() * 8 + state.bloch.size * 8 + ref.numel() * 8   # POVM probabilities' inputs and the centre state
+    e2e_levels = np.linspace(1e-3, 1 - 1e-3, 1000)                      # ConfidenceInterval.__call__'s default levels
+    traffic0 = dict(qpar.TRAFFIC)
     e2e_times = []
     for i in range(1 + e2e_steps):
         barrier()
@@ -317,10 +332,12 @@ def run_ours(args, rank, local_rank, world):
         itv = qp.BootstrapStateInterval(tmg, n_points=B * world, method=args.method, tol=args.tol,
                                         max_iter=args.max_iter, state=state)
         itv.setup(seed=seed + 100 + i)
-        _ = itv.cl_to_dist(0.95)
+        _ = itv.cl_to_dist(e2e_levels)   # the result a user reads: distances at the confidence levels, on the host
         barrier()
         if i > 0:
             e2e_times.append(time.perf_counter() - t0)
+    h2d += (qpar.TRAFFIC["h2d"] - traffic0["h2d"]) // (1 + e2e_steps)
+    d2h = (qpar.TRAFFIC["d2h"] - traffic0["d2h"]) // (1 + e2e_steps)
     e2e_s = max_over_ranks(float(np.sum(e2e_times)))
     e2e_value = world * B * e2e_steps / e2e_s
     clock_info = clocks.stop() if rank == 0 else None

@@ -49,9 +49,12 @@ def all_gather_concat(local, n_total):
     import torch.distributed as dist
 
     width = -(-int(n_total) // size)
+    gathered = torch.empty((size * width,), dtype=local.dtype, device=local.device)
+    if int(n_total) == size * width:  # equal shards: the gathered buffer already is the concatenation
+        dist.all_gather_into_tensor(gathered, local.contiguous())
+        return gathered
     padded = torch.zeros((width,), dtype=local.dtype, device=local.device)
     padded[: local.numel()] = local
-    gathered = torch.empty((size * width,), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(gathered, padded)
     pieces = []
     for r in range(size):
@@ -59,6 +62,9 @@ def all_gather_concat(local, n_total):
         pieces.append(gathered[r * width: r * width + (hi - lo)])
     return torch.cat(pieces)
 
+
+# bytes that crossed PCIe through this module since import (bench.py reads the difference around a call)
+TRAFFIC = {"d2h": 0, "h2d": 0}
 
 _PINNED = {}
 
@@ -78,23 +84,41 @@ def to_host_pinned(tensor):
         buf = _PINNED[key] = torch.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
     buf.copy_(tensor, non_blocking=True)
     torch.cuda.current_stream().synchronize()
+    TRAFFIC["d2h"] += tensor.numel() * tensor.element_size()
     return buf.numpy().copy()
 
 
 class QuantileFunction:
     """Linear interpolant of the sorted bootstrap distances on the grid linspace(0, 1, N) -- the object the
     reference builds with scipy.interpolate.interp1d(conf_levels, dist) (quantpy/tomography/interval.py:610-612).
-    Same call semantics (vectorised, ValueError outside [0, 1]) and the same `.x` / `.y` attributes, but
-    nothing of size N is built until it is asked for, which keeps the end-to-end bootstrap call short."""
+    Same call semantics (vectorised, ValueError outside [0, 1]) and the same `.x` / `.y` attributes.
+
+    The sorted values may stay ON THE DEVICE: a call then fetches only the two neighbours of every requested
+    level (a few KB), and nothing of size N crosses PCIe unless `.y` (or the interval's `.dist`) is asked for."""
 
     def __init__(self, sorted_values):
-        self.y = np.asarray(sorted_values, dtype=np.float64)
+        self._dev = None
+        self._y = None
+        if hasattr(sorted_values, "is_cuda") and sorted_values.is_cuda:
+            self._dev = sorted_values
+            self._n = int(sorted_values.numel())
+        else:
+            if hasattr(sorted_values, "numpy"):
+                sorted_values = sorted_values.numpy()
+            self._y = np.asarray(sorted_values, dtype=np.float64)
+            self._n = len(self._y)
         self._x = None
+
+    @property
+    def y(self):
+        if self._y is None:
+            self._y = to_host_pinned(self._dev)
+        return self._y
 
     @property
     def x(self):
         if self._x is None:
-            self._x = np.linspace(0, 1, len(self.y))
+            self._x = np.linspace(0, 1, self._n)
         return self._x
 
     def __call__(self, levels):
@@ -103,17 +127,30 @@ class QuantileFunction:
             raise ValueError("A value in x_new is below the interpolation range.")
         if np.any(levels > 1):
             raise ValueError("A value in x_new is above the interpolation range.")
-        n = len(self.y)
+        n = self._n
         if n == 1:
             return np.full(levels.shape, self.y[0])
         pos = levels * (n - 1)
         lo = np.minimum(np.floor(pos).astype(np.int64), n - 2)
         frac = pos - lo
-        return self.y[lo] + (self.y[lo + 1] - self.y[lo]) * frac
+        if self._y is None:
+            import torch
+
+            idx = torch.from_numpy(np.concatenate([lo.reshape(-1), lo.reshape(-1) + 1])).to(self._dev.device)
+            pair = self._dev[idx].cpu().numpy()
+            TRAFFIC["h2d"] += idx.numel() * 8
+            TRAFFIC["d2h"] += pair.size * 8
+            y_lo, y_hi = pair[: lo.size].reshape(lo.shape), pair[lo.size:].reshape(lo.shape)
+        else:
+            y_lo, y_hi = self._y[lo], self._y[lo + 1]
+        return y_lo + (y_hi - y_lo) * frac
 
 
 def quantile_function(dist_values, presorted=False):
-    """Sorted distances -> interpolant of (linspace(0, 1, N), dist) as quantpy/tomography/interval.py:610-612."""
+    """Sorted distances -> interpolant of (linspace(0, 1, N), dist) as quantpy/tomography/interval.py:610-612.
+    A CUDA tensor stays on the device (sorted there if needed)."""
+    if hasattr(dist_values, "is_cuda") and dist_values.is_cuda:
+        return QuantileFunction(dist_values if presorted else dist_values.sort().values)
     ordered = np.asarray(dist_values, dtype=np.float64)
     if not presorted:
         ordered = np.sort(ordered)

@@ -58,9 +58,13 @@ class ConfidenceInterval(ABC):
     def _finish(self, local_dist, n_points):
         """All-gather the per-rank distances, keep them (sorted) and build the quantile function."""
         full = parallel.all_gather_concat(local_dist, n_points)
-        ordered = full.sort().values  # sort on the device, then one D2H copy of N doubles through pinned memory
-        self.dist = parallel.to_host_pinned(ordered)
-        self.cl_to_dist = parallel.quantile_function(self.dist, presorted=True)
+        # sorted on the device and left there: the quantile function fetches what a call needs, `dist` the rest
+        self.cl_to_dist = parallel.quantile_function(full.sort().values, presorted=True)
+
+    @property
+    def dist(self):
+        """The sorted distances behind `cl_to_dist` (host array; copied from the device on first use)."""
+        return self.cl_to_dist.y
 
 
 class MomentInterval(ConfidenceInterval):
@@ -133,7 +137,8 @@ class BootstrapStateInterval(ConfidenceInterval):
         method = "mle" if self.method == "mle-constr" else self.method  # same maximiser, same kernel
         rank, size = parallel.world()
         lo, hi = parallel.shard_bounds(self.n_points, rank, size)
-        seed = parallel.broadcast_seed(engine.next_seed() if seed is None else int(seed))
+        # a key drawn from this rank's np.random stream must be agreed on; an explicit seed is the caller's (SPMD)
+        seed = parallel.broadcast_seed(engine.next_seed()) if seed is None else int(seed)
         plan = engine.state_plan(self.tmg.povm_matrix, self.tmg.n_measurements)
         probs = plan.probabilities(self.state.bloch)[0]
         kind = dst_kind(self.tmg.dst)
@@ -201,13 +206,9 @@ class MHMCStateInterval(ConfidenceInterval):
 
             mats = nt.complex_to_host(samples)
             dist = np.sort([float(self.tmg.dst(Qobj(m), self.state)) for m in mats])
-            self.dist = dist
             self.cl_to_dist = parallel.quantile_function(dist, presorted=True)
             return
-        local = engine.distance(samples, self.state.matrix, kind)
-        ordered = local.sort().values
-        self.dist = parallel.to_host_pinned(ordered)
-        self.cl_to_dist = parallel.quantile_function(self.dist, presorted=True)
+        self.cl_to_dist = parallel.quantile_function(engine.distance(samples, self.state.matrix, kind))
 
 
 class BootstrapProcessInterval(ConfidenceInterval):
@@ -230,7 +231,7 @@ class BootstrapProcessInterval(ConfidenceInterval):
             raise ValueError("Incorrect value for argument `method`")
         rank, size = parallel.world()
         lo, hi = parallel.shard_bounds(self.n_points, rank, size)
-        seed = parallel.broadcast_seed(engine.next_seed() if seed is None else int(seed))
+        seed = parallel.broadcast_seed(engine.next_seed()) if seed is None else int(seed)
         first = self.tmg.tomographs[0]
         boot = self.tmg.__class__(self.channel, self.tmg.input_states, self.tmg.dst)
         centre = self.channel.choi.matrix
