@@ -16,7 +16,6 @@ namespace qpb {
 
 constexpr int kMhmcWarps = 4;
 constexpr int kMhmcMaxD = 256;  // n <= 4
-constexpr int kMhmcMaxKJ = 8;   // K <= 256 outcomes held as frequencies in registers (n <= 2 'proj', n = 3 'proj-set' ...)
 
 // packed Cholesky vector (routines.py:84-101): d diagonal entries, then Re and Im of the strict lower triangle in
 // np.tril_indices order
@@ -31,7 +30,7 @@ __device__ __forceinline__ double chol_im(const double* x, int d, int i, int j) 
 // p = Tr(E_k L L^dagger) / Tr(L L^dagger)  (state.py:217-229)
 // hw = h with the off-diagonal entries doubled: Tr(E rho) = sum_e packed(E)[e] hw[e] for Hermitian E, rho.
 __device__ double log_target(const double* x, double* h, double* hw, int d, int D, int K, const double* __restrict__ Ar,
-                             const double (&fk)[kMhmcMaxKJ], int lane) {
+                             const double* fk, int lane) {
     for (int e = lane; e < D; e += 32) {
         const int a = e / d, b = e % d;
         const int lo = min(a, b), hi = max(a, b);
@@ -50,15 +49,11 @@ __device__ double log_target(const double* x, double* h, double* hw, int d, int 
     double tr = 0.0;
     for (int a = 0; a < d; ++a) tr += h[a * d + a];
     double acc = 0.0;
-#pragma unroll
-    for (int jj = 0; jj < kMhmcMaxKJ; ++jj) {
-        const int k = lane + 32 * jj;
-        if (k < K) {
-            const double* row = Ar + (size_t)k * D;
-            double p = 0.0;
-            for (int e = 0; e < D; ++e) p = fma(row[e], hw[e], p);
-            acc = fma(fk[jj], log(p / tr + kLogGuard), acc);
-        }
+    for (int k = lane; k < K; k += 32) {
+        const double* row = Ar + (size_t)k * D;
+        double p = 0.0;
+        for (int e = 0; e < D; ++e) p = fma(row[e], hw[e], p);
+        acc = fma(fk[k], log(p / tr + kLogGuard), acc);
     }
     __syncwarp();
     return warp_sum(acc);
@@ -72,10 +67,11 @@ k_mhmc_state(int d, int D, int K, int C, int n_samples, int thinning, int burn_s
              double* __restrict__ x_final) {
     extern __shared__ __align__(16) double sm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* x = sm + (size_t)warp * 4 * D;
+    double* x = sm + (size_t)warp * (4 * D + K);
     double* xp = x + D;
     double* h = xp + D;
     double* hw = h + D;
+    double* fk = hw + D;  // the chain's K frequencies
     const long total_steps = (long)burn_steps + (long)n_samples * thinning;
     for (int c = blockIdx.x * kMhmcWarps + warp; c < C; c += gridDim.x * kMhmcWarps) {
         const int32_t* cnt = counts + (counts_batched ? (size_t)c * K : 0);
@@ -83,12 +79,7 @@ k_mhmc_state(int d, int D, int K, int C, int n_samples, int thinning, int burn_s
         for (int k = lane; k < K; k += 32) tot += cnt[k];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        double fk[kMhmcMaxKJ];
-#pragma unroll
-        for (int jj = 0; jj < kMhmcMaxKJ; ++jj) {
-            const int k = lane + 32 * jj;
-            fk[jj] = k < K ? (double)cnt[k] / (double)tot : 0.0;
-        }
+        for (int k = lane; k < K; k += 32) fk[k] = (double)cnt[k] / (double)tot;
         for (int e = lane; e < D; e += 32) x[e] = x_init[(size_t)c * D + e];
         __syncwarp();
         double cur = log_target(x, h, hw, d, D, K, Ar, fk, lane);
@@ -166,12 +157,14 @@ extern "C" int qpb_mhmc_state(const qpb_state_plan* plan, int C, int n_samples, 
     QPB_REQUIRE(C >= 0 && n_samples >= 0 && burn_steps >= 0, "negative size");
     QPB_REQUIRE(thinning >= 1, "thinning must be >= 1");
     QPB_REQUIRE(plan->D <= kMhmcMaxD, "n_qubits=%d unsupported by the MHMC kernel", plan->n);
-    QPB_REQUIRE(plan->K <= 32 * kMhmcMaxKJ, "K=%d outcomes exceed the MHMC kernel's %d", plan->K, 32 * kMhmcMaxKJ);
     QPB_REQUIRE((deltas == nullptr) == (uniforms == nullptr), "deltas and uniforms must be given together");
     if (C == 0) return QPB_OK;
     QPB_REQUIRE(counts && x_init && (samples || n_samples == 0), "NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = sizeof(double) * 4 * plan->D * kMhmcWarps;
+    const size_t smem = sizeof(double) * (4 * (size_t)plan->D + plan->K) * kMhmcWarps;
+    QPB_REQUIRE(smem <= 200 * 1024, "POVM with K=%d outcomes too large for the MHMC kernel", plan->K);
+    if (smem > 48 * 1024)
+        QPB_CUDA(cudaFuncSetAttribute(k_mhmc_state, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long blocks = ((long)C + kMhmcWarps - 1) / kMhmcWarps;
     const long cap = (long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
