@@ -1,5 +1,5 @@
 // Structured R.rho.R maximum likelihood for n = 3, 4 qubits and Pauli-axis POVMs ('proj', 'proj-set',
-// 'proj4', any shot weights): ONE WARP PER SAMPLE, all state in shared memory.
+// 'proj4', any shot weights): ONE CTA (2 or 4 warps) PER SAMPLE, all state in shared memory.
 //
 // Every effect is E_k = c_k (x)_q (1 + s_q sigma_{a_q}), a_q in {X,Y,Z}.  With S_i = Tr(sigma_i rho)
 // (i = base-4 Pauli string) the probabilities follow from n successive per-qubit "axis" maps
@@ -26,8 +26,16 @@ struct Axis {
     static constexpr int D = d * d;          // 4^N
     static constexpr int K6 = ipow(6, N);    // canonical slots
     static constexpr int ld = d + 1;         // padded leading dimension of the complex matrices (bank conflicts)
-    // doubles of shared memory per warp: rho, R, W (complex d x ld each) + two contraction buffers + f
-    static constexpr int per_warp = 3 * 2 * d * ld + 3 * K6;
+    // The two contraction buffers hold at most [6^(N-1)][4] reals: the last axis stage, the reciprocals and the
+    // first adjoint stage are fused in registers, so the 6^N probabilities are never stored.  The transform /
+    // product workspaces alias them (their lifetimes do not overlap), the counts stay int32.
+    static constexpr int buf = ipow(6, N - 1) * 4;
+    static_assert(2 * d * ld <= buf, "matrix workspaces must fit in a contraction buffer");
+    // bytes of shared memory per sample: rho, R (complex d x ld), two buffers, counts
+    static constexpr size_t smem_bytes = sizeof(double) * (2 * 2 * d * ld + 2 * buf) + sizeof(int) * K6;
+    // resident CTAs per SM the launch bounds ask for (register cap), CTA size
+    static constexpr int GS = (N == 4) ? 128 : 64;
+    static constexpr int min_blocks = (N == 4) ? 7 : 16;
 };
 
 // One sample is processed by a group of GS threads: a warp (GS = 32) or a whole CTA (GS = blockDim.x).
@@ -64,7 +72,13 @@ __device__ __forceinline__ int interleave(int a, int b) {
     return e;
 }
 
-// forward fast Pauli transform, in place on W (complex, digit-interleaved): W[i] <- Tr(sigma_i M)
+// Position of transform element i in the workspace: a GF(2)-linear bank swizzle of the low three index bits
+// (b0 ^= b4, b1 ^= b3, b2 ^= b4) that makes the eight lanes of a quarter-warp hit eight different 16-byte bank
+// groups in every radix-4 stage (lanes differ in index bits {0,1,2}, {0,1,4} or {2,3,4} depending on the stride);
+// the plain layout cost 2x (stride 4) and 4x (stride 1) the wavefronts.
+__device__ __forceinline__ int tw(int i) { return i ^ (((i >> 4) & 1) * 5) ^ (((i >> 3) & 1) << 1); }
+
+// forward fast Pauli transform, in place on W (complex, digit-interleaved, swizzled by tw): W[i] <- Tr(sigma_i M)
 template <int N, int GS>
 __device__ __forceinline__ void pauli_forward(double2* __restrict__ W, int lane) {
     constexpr int D = Axis<N>::D;
@@ -73,11 +87,12 @@ __device__ __forceinline__ void pauli_forward(double2* __restrict__ W, int lane)
         const int stride = 1 << (2 * (N - 1 - q));
         for (int g = lane; g < D / 4; g += GS) {
             const int idx = (g / stride) * 4 * stride + (g % stride);
-            const double2 v0 = W[idx], v1 = W[idx + stride], v2 = W[idx + 2 * stride], v3 = W[idx + 3 * stride];
-            W[idx] = make_double2(v0.x + v3.x, v0.y + v3.y);                   // I
-            W[idx + stride] = make_double2(v1.x + v2.x, v1.y + v2.y);          // X
-            W[idx + 2 * stride] = make_double2(-(v1.y - v2.y), v1.x - v2.x);   // Y = i (v1 - v2)
-            W[idx + 3 * stride] = make_double2(v0.x - v3.x, v0.y - v3.y);      // Z
+            const int i0 = tw(idx), i1 = tw(idx + stride), i2 = tw(idx + 2 * stride), i3 = tw(idx + 3 * stride);
+            const double2 v0 = W[i0], v1 = W[i1], v2 = W[i2], v3 = W[i3];
+            W[i0] = make_double2(v0.x + v3.x, v0.y + v3.y);          // I
+            W[i1] = make_double2(v1.x + v2.x, v1.y + v2.y);          // X
+            W[i2] = make_double2(-(v1.y - v2.y), v1.x - v2.x);       // Y = i (v1 - v2)
+            W[i3] = make_double2(v0.x - v3.x, v0.y - v3.y);          // Z
         }
         gsync<GS>();
     }
@@ -92,11 +107,12 @@ __device__ __forceinline__ void pauli_inverse(double2* __restrict__ W, int lane)
         const int stride = 1 << (2 * (N - 1 - q));
         for (int g = lane; g < D / 4; g += GS) {
             const int idx = (g / stride) * 4 * stride + (g % stride);
-            const double2 gi = W[idx], gx = W[idx + stride], gy = W[idx + 2 * stride], gz = W[idx + 3 * stride];
-            W[idx] = make_double2(gi.x + gz.x, gi.y + gz.y);                   // (0,0)
-            W[idx + stride] = make_double2(gx.x + gy.y, gx.y - gy.x);          // (0,1) = gx - i gy
-            W[idx + 2 * stride] = make_double2(gx.x - gy.y, gx.y + gy.x);      // (1,0) = gx + i gy
-            W[idx + 3 * stride] = make_double2(gi.x - gz.x, gi.y - gz.y);      // (1,1)
+            const int i0 = tw(idx), i1 = tw(idx + stride), i2 = tw(idx + 2 * stride), i3 = tw(idx + 3 * stride);
+            const double2 gi = W[i0], gx = W[i1], gy = W[i2], gz = W[i3];
+            W[i0] = make_double2(gi.x + gz.x, gi.y + gz.y);          // (0,0)
+            W[i1] = make_double2(gx.x + gy.y, gx.y - gy.x);          // (0,1) = gx - i gy
+            W[i2] = make_double2(gx.x - gy.y, gx.y + gy.x);          // (1,0) = gx + i gy
+            W[i3] = make_double2(gi.x - gz.x, gi.y - gz.y);          // (1,1)
         }
         gsync<GS>();
     }
@@ -129,16 +145,17 @@ __device__ __forceinline__ void axis_adjoint(const double* __restrict__ in, doub
     gsync<GS>();
 }
 
+// stages 0 .. N-2 (the last one is fused with the reciprocals, below)
 template <int N, int GS, int Q = 0>
 __device__ __forceinline__ double* axis_forward_all(double* a, double* b, int lane) {
-    if constexpr (Q == N) {
+    if constexpr (Q == N - 1) {
         return a;  // result lives in `a`
     } else {
         axis_forward<N, Q, GS>(a, b, lane);
         return axis_forward_all<N, GS, Q + 1>(b, a, lane);
     }
 }
-template <int N, int GS, int Q = N - 1>
+template <int N, int GS, int Q = N - 2>
 __device__ __forceinline__ double* axis_adjoint_all(double* a, double* b, int lane) {
     if constexpr (Q < 0) {
         return a;
@@ -148,37 +165,76 @@ __device__ __forceinline__ double* axis_adjoint_all(double* a, double* b, int la
     }
 }
 
-// C = X * Y for d x d complex matrices in shared memory (row-major); each lane owns whole output elements
+// Last axis stage, weights and first adjoint stage in one pass over [6^(N-1)] prefixes:
+//   p(pre, a, +-) = in[pre][I] +- in[pre][a];  w = f / (p + eps);  out[pre][I] = sum w,  out[pre][a] = w+ - w-
+template <int N, int GS>
+__device__ __forceinline__ void axis_last_fused(const double* __restrict__ in, double* __restrict__ out,
+                                                const int* __restrict__ cnt, const double* __restrict__ epsp,
+                                                double inv_total, int lane) {
+    constexpr int PRE = ipow(6, N - 1);
+    for (int pre = lane; pre < PRE; pre += GS) {
+        const double x0 = in[pre * 4];
+        double u0 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double xa = in[pre * 4 + a + 1];
+            const int slot = pre * 6 + 2 * a;
+            const double wp = ((double)cnt[slot] * inv_total) * fast_recip((x0 + xa) + epsp[slot]);
+            const double wm = ((double)cnt[slot + 1] * inv_total) * fast_recip((x0 - xa) + epsp[slot + 1]);
+            u0 += wp + wm;
+            out[pre * 4 + a + 1] = wp - wm;
+        }
+        out[pre * 4] = u0;
+    }
+    gsync<GS>();
+}
+
+// C = X * Y for d x d complex matrices in shared memory (row-major, leading dimension ld = d + 1).
+// The kernel is bound by shared-memory wavefronts (ncu: 93 % of the LSU data pipe, 40 % of them from the Y loads of
+// this routine), so at n = 4 every lane owns a 2 x 4 register tile (rows a and a + d/2): 4 Y loads and 2 X loads
+// feed 8 complex multiply-adds.  Lanes of a quarter-warp share the column block (their Y address is one broadcast)
+// and differ in the row, whose stride of ld complex numbers keeps the X loads conflict-free.
 template <int N, int GS>
 __device__ __forceinline__ void cmatmul(double2* __restrict__ C, const double2* __restrict__ X,
                                         const double2* __restrict__ Y, int lane) {
-    constexpr int d = Axis<N>::d, D = Axis<N>::D, ld = Axis<N>::ld;
-    constexpr int TJ = (D / 32 >= 4) ? 4 : (D / 32 >= 2 ? 2 : 1);  // outputs per lane per pass (same row)
-    for (int t = lane; t < D / TJ; t += GS) {
-        const int a = t / (d / TJ), b0 = (t % (d / TJ)) * TJ;
-        double re[TJ], im[TJ];
+    constexpr int d = Axis<N>::d, ld = Axis<N>::ld;
+    // n = 4: 2 x 4 tiles (32 tasks, shared-memory bound); n = 3: 1 x 2 tiles (32 tasks, latency bound: keep lanes busy)
+    constexpr int TI = (d >= 16) ? 2 : 1, TJ = (d >= 16) ? 4 : 2, ROWS = d / TI;
+    constexpr int TASKS = ROWS * (d / TJ);
+    for (int t = lane; t < TASKS; t += GS) {
+        const int a = t % ROWS, b0 = (t / ROWS) * TJ;
+        double re[TI][TJ], im[TI][TJ];
 #pragma unroll
-        for (int j = 0; j < TJ; ++j) re[j] = im[j] = 0.0;
-#pragma unroll 4
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) re[i][j] = im[i][j] = 0.0;
+#pragma unroll 2
         for (int c = 0; c < d; ++c) {
-            const double2 x = X[a * ld + c];
+            double2 x[TI];
+#pragma unroll
+            for (int i = 0; i < TI; ++i) x[i] = X[(a + i * ROWS) * ld + c];
 #pragma unroll
             for (int j = 0; j < TJ; ++j) {
                 const double2 y = Y[c * ld + b0 + j];
-                re[j] = fma(x.x, y.x, re[j]);
-                re[j] = fma(-x.y, y.y, re[j]);
-                im[j] = fma(x.x, y.y, im[j]);
-                im[j] = fma(x.y, y.x, im[j]);
+#pragma unroll
+                for (int i = 0; i < TI; ++i) {
+                    re[i][j] = fma(x[i].x, y.x, re[i][j]);
+                    re[i][j] = fma(-x[i].y, y.y, re[i][j]);
+                    im[i][j] = fma(x[i].x, y.y, im[i][j]);
+                    im[i][j] = fma(x[i].y, y.x, im[i][j]);
+                }
             }
         }
 #pragma unroll
-        for (int j = 0; j < TJ; ++j) C[a * ld + b0 + j] = make_double2(re[j], im[j]);
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) C[(a + i * ROWS) * ld + b0 + j] = make_double2(re[i][j], im[i][j]);
     }
     gsync<GS>();
 }
 
 template <int N, int GS>
-__global__ void __launch_bounds__(GS)
+__global__ void __launch_bounds__(GS, Axis<N>::min_blocks)
 k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* __restrict__ epsp,
                const int32_t* __restrict__ counts, const double* __restrict__ rho0, int max_iter, double tol,
                double* __restrict__ rho_out, int32_t* __restrict__ iters, unsigned int* __restrict__ queue) {
@@ -187,12 +243,13 @@ k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* 
     __shared__ double red[32];
     __shared__ unsigned int next_sample;
     const int lane = threadIdx.x;  // index within the group (= CTA)
+    constexpr int BUF = Axis<N>::buf;
     double2* rho = reinterpret_cast<double2*>(smd);    // [d][ld]
     double2* Rm = rho + d * ld;                        // [d][ld]
-    double2* W = Rm + d * ld;                          // transform workspace (dense D) / product (padded)
-    double* bufA = reinterpret_cast<double*>(W + d * ld);
-    double* bufB = bufA + K6;
-    double* f = bufB + K6;
+    double* bufA = reinterpret_cast<double*>(Rm + d * ld);
+    double* bufB = bufA + BUF;
+    int* cnt = reinterpret_cast<int*>(bufB + BUF);     // counts in canonical slot order
+    double2* W = reinterpret_cast<double2*>(bufB);     // transform workspace (dense D) / product (padded): aliases bufB
 
     for (;;) {
         __syncthreads();
@@ -205,9 +262,10 @@ k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* 
         long long tot_i = 0;
         for (int k = lane; k < K; k += GS) tot_i += c[k];
         const double total = gsum<GS>((double)tot_i, red, lane);
-        for (int e = lane; e < K6; e += GS) f[e] = 0.0;
+        const double inv_total = 1.0 / total;
+        for (int e = lane; e < K6; e += GS) cnt[e] = 0;
         gsync<GS>();
-        for (int k = lane; k < K; k += GS) f[slot_of_col[k]] = (double)c[k] / total;
+        for (int k = lane; k < K; k += GS) cnt[slot_of_col[k]] = c[k];
         if (rho0) {
             const double2* r0 = reinterpret_cast<const double2*>(rho0) + (size_t)b * D;
             for (int e = lane; e < D; e += GS) {  // Hermitian part of the start, as the packed kernels take it
@@ -223,19 +281,28 @@ k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* 
         int it = 0;
         for (it = 1; it <= max_iter; ++it) {
             // S_i = Tr(sigma_i rho)
-            for (int e = lane; e < D; e += GS) W[interleave<N>(e / d, e % d)] = rho[(e / d) * ld + e % d];
+            for (int e = lane; e < D; e += GS) W[tw(interleave<N>(e / d, e % d))] = rho[(e / d) * ld + e % d];
             gsync<GS>();
             pauli_forward<N, GS>(W, lane);
-            for (int e = lane; e < D; e += GS) bufA[e] = W[e].x;
+            for (int e = lane; e < D; e += GS) bufA[e] = W[tw(e)].x;
             gsync<GS>();
-            double* q = axis_forward_all<N, GS>(bufA, bufB, lane);  // q[slot] = p_slot / c_slot
-            for (int e = lane; e < K6; e += GS) q[e] = f[e] * fast_recip(q[e] + epsp[e]);
-            gsync<GS>();
-            double* g = axis_adjoint_all<N, GS>(q, q == bufA ? bufB : bufA, lane);  // Pauli coefficients of R
-            for (int e = lane; e < D; e += GS) W[e] = make_double2(g[e], 0.0);
-            gsync<GS>();
+            double* q = axis_forward_all<N, GS>(bufA, bufB, lane);  // after N-1 stages: [6^(N-1)][4]
+            double* u = q == bufA ? bufB : bufA;
+            axis_last_fused<N, GS>(q, u, cnt, epsp, inv_total, lane);
+            double* g = axis_adjoint_all<N, GS>(u, q, lane);  // Pauli coefficients of R
+            {  // g may live in the buffer W aliases: pass the coefficients through registers
+                constexpr int PER = (D + GS - 1) / GS;
+                double gv[PER];
+#pragma unroll
+                for (int j = 0; j < PER; ++j) gv[j] = (lane + j * GS < D) ? g[lane + j * GS] : 0.0;
+                gsync<GS>();
+#pragma unroll
+                for (int j = 0; j < PER; ++j)
+                    if (lane + j * GS < D) W[tw(lane + j * GS)] = make_double2(gv[j], 0.0);
+                gsync<GS>();
+            }
             pauli_inverse<N, GS>(W, lane);
-            for (int e = lane; e < D; e += GS) Rm[(e / d) * ld + e % d] = W[interleave<N>(e / d, e % d)];
+            for (int e = lane; e < D; e += GS) Rm[(e / d) * ld + e % d] = W[tw(interleave<N>(e / d, e % d))];
             gsync<GS>();
             cmatmul<N, GS>(W, Rm, rho, lane);   // W = R rho
             double2* T = reinterpret_cast<double2*>(bufA);  // 2*d*ld doubles fit in one contraction buffer (<= 6^N)
@@ -325,9 +392,10 @@ static bool detect_axis(const double* A, int n, int K, int* slot_of_col, double*
 template <int N>
 static int launch_axis(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                        double tol, double* rho, int32_t* iters, cudaStream_t st) {
-    // one CTA of GS threads per sample: 4 CTAs (16 warps) per SM at n = 4 instead of 4 lone warps
-    constexpr int GS = (N == 4) ? 128 : 64;
-    const size_t smem = sizeof(double) * (size_t)Axis<N>::per_warp;
+    // one CTA of GS threads per sample; shared memory (27.7 KB at n = 4) and the register cap of the launch bounds
+    // allow 7 resident CTAs per SM at n = 4, 16 at n = 3
+    constexpr int GS = Axis<N>::GS;
+    const size_t smem = Axis<N>::smem_bytes;
     QPB_REQUIRE(smem <= 227 * 1024, "axis kernel needs %zu bytes of shared memory", smem);
     auto kern = k_mle_rrr_axis<N, GS>;
     if (smem > 48 * 1024) QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
