@@ -78,54 +78,132 @@ __device__ __forceinline__ int interleave(int a, int b) {
 // the plain layout cost 2x (stride 4) and 4x (stride 1) the wavefronts.
 __device__ __forceinline__ int tw(int i) { return i ^ (((i >> 4) & 1) * 5) ^ (((i >> 3) & 1) << 1); }
 
-// forward fast Pauli transform, in place on W (complex, digit-interleaved, swizzled by tw): W[i] <- Tr(sigma_i M)
+// (row, column) of the matrix element stored at digit-interleaved position e
+template <int N>
+__device__ __forceinline__ void deinterleave(int e, int& a, int& b) {
+    a = 0;
+    b = 0;
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+        const int dig = (e >> (2 * (N - 1 - q))) & 3;
+        a = a * 2 + (dig >> 1);
+        b = b * 2 + (dig & 1);
+    }
+}
+
+// Forward fast Pauli transform S_i = Tr(sigma_i M), one radix-4 stage per qubit.  The first stage reads the matrix
+// M (row-major, leading dimension ld) directly, the middle stages run in place on the swizzled workspace W, the
+// last one writes only what is needed afterwards: the real parts, in natural order, to S.
 template <int N, int GS>
-__device__ __forceinline__ void pauli_forward(double2* __restrict__ W, int lane) {
-    constexpr int D = Axis<N>::D;
+__device__ __forceinline__ void pauli_forward(const double2* __restrict__ M, double2* __restrict__ W,
+                                              double* __restrict__ S, int lane) {
+    constexpr int D = Axis<N>::D, ld = Axis<N>::ld;
 #pragma unroll
     for (int q = 0; q < N; ++q) {
         const int stride = 1 << (2 * (N - 1 - q));
         for (int g = lane; g < D / 4; g += GS) {
             const int idx = (g / stride) * 4 * stride + (g % stride);
-            const int i0 = tw(idx), i1 = tw(idx + stride), i2 = tw(idx + 2 * stride), i3 = tw(idx + 3 * stride);
-            const double2 v0 = W[i0], v1 = W[i1], v2 = W[i2], v3 = W[i3];
-            W[i0] = make_double2(v0.x + v3.x, v0.y + v3.y);          // I
-            W[i1] = make_double2(v1.x + v2.x, v1.y + v2.y);          // X
-            W[i2] = make_double2(-(v1.y - v2.y), v1.x - v2.x);       // Y = i (v1 - v2)
-            W[i3] = make_double2(v0.x - v3.x, v0.y - v3.y);          // Z
+            double2 v0, v1, v2, v3;
+            if (q == 0) {
+                int al, bl;
+                deinterleave<N>(idx, al, bl);  // low bits of (row, column); the first qubit's digit selects the block
+                constexpr int H = 1 << (N - 1);
+                v0 = M[al * ld + bl];
+                v1 = M[al * ld + bl + H];
+                v2 = M[(al + H) * ld + bl];
+                v3 = M[(al + H) * ld + bl + H];
+            } else {
+                v0 = W[tw(idx)];
+                v1 = W[tw(idx + stride)];
+                v2 = W[tw(idx + 2 * stride)];
+                v3 = W[tw(idx + 3 * stride)];
+            }
+            if (q == N - 1) {
+                S[idx] = v0.x + v3.x;        // I
+                S[idx + 1] = v1.x + v2.x;    // X
+                S[idx + 2] = v2.y - v1.y;    // Y = Re i (v1 - v2)
+                S[idx + 3] = v0.x - v3.x;    // Z
+            } else {
+                W[tw(idx)] = make_double2(v0.x + v3.x, v0.y + v3.y);                     // I
+                W[tw(idx + stride)] = make_double2(v1.x + v2.x, v1.y + v2.y);            // X
+                W[tw(idx + 2 * stride)] = make_double2(-(v1.y - v2.y), v1.x - v2.x);     // Y = i (v1 - v2)
+                W[tw(idx + 3 * stride)] = make_double2(v0.x - v3.x, v0.y - v3.y);        // Z
+            }
         }
         gsync<GS>();
     }
 }
 
-// inverse: W[i] = g_i (complex) -> W[e(a,b)] = (sum_i g_i sigma_i)[a][b]
+// Inverse: real Pauli coefficients g (natural order) -> M = sum_i g_i sigma_i (row-major, leading dimension ld).
+// g may live in the buffer W aliases, so the first stage reads its quad into registers before anything is written.
 template <int N, int GS>
-__device__ __forceinline__ void pauli_inverse(double2* __restrict__ W, int lane) {
-    constexpr int D = Axis<N>::D;
+__device__ __forceinline__ void pauli_inverse(const double* __restrict__ gcoef, double2* __restrict__ W,
+                                              double2* __restrict__ M, int lane) {
+    constexpr int D = Axis<N>::D, ld = Axis<N>::ld;
+    static_assert(D / 4 <= GS, "one quad per thread in the first stage");
+    {
+        constexpr int stride = 1 << (2 * (N - 1));
+        double gi = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+        if (lane < D / 4) {
+            gi = gcoef[lane];
+            gx = gcoef[lane + stride];
+            gy = gcoef[lane + 2 * stride];
+            gz = gcoef[lane + 3 * stride];
+        }
+        gsync<GS>();
+        if (lane < D / 4) {
+            W[tw(lane)] = make_double2(gi + gz, 0.0);                // (0,0)
+            W[tw(lane + stride)] = make_double2(gx, -gy);            // (0,1) = gx - i gy
+            W[tw(lane + 2 * stride)] = make_double2(gx, gy);         // (1,0) = gx + i gy
+            W[tw(lane + 3 * stride)] = make_double2(gi - gz, 0.0);   // (1,1)
+        }
+        gsync<GS>();
+    }
 #pragma unroll
-    for (int q = 0; q < N; ++q) {
+    for (int q = 1; q < N; ++q) {
         const int stride = 1 << (2 * (N - 1 - q));
         for (int g = lane; g < D / 4; g += GS) {
             const int idx = (g / stride) * 4 * stride + (g % stride);
-            const int i0 = tw(idx), i1 = tw(idx + stride), i2 = tw(idx + 2 * stride), i3 = tw(idx + 3 * stride);
-            const double2 gi = W[i0], gx = W[i1], gy = W[i2], gz = W[i3];
-            W[i0] = make_double2(gi.x + gz.x, gi.y + gz.y);          // (0,0)
-            W[i1] = make_double2(gx.x + gy.y, gx.y - gy.x);          // (0,1) = gx - i gy
-            W[i2] = make_double2(gx.x - gy.y, gx.y + gy.x);          // (1,0) = gx + i gy
-            W[i3] = make_double2(gi.x - gz.x, gi.y - gz.y);          // (1,1)
+            const double2 gi = W[tw(idx)], gx = W[tw(idx + stride)], gy = W[tw(idx + 2 * stride)],
+                          gz = W[tw(idx + 3 * stride)];
+            const double2 m00 = make_double2(gi.x + gz.x, gi.y + gz.y);
+            const double2 m01 = make_double2(gx.x + gy.y, gx.y - gy.x);  // gx - i gy
+            const double2 m10 = make_double2(gx.x - gy.y, gx.y + gy.x);  // gx + i gy
+            const double2 m11 = make_double2(gi.x - gz.x, gi.y - gz.y);
+            if (q == N - 1) {  // idx = 4 * (digits of the other qubits): the last qubit is the lowest bit of row and column
+                int a, b;
+                deinterleave<N>(idx, a, b);
+                M[a * ld + b] = m00;
+                M[a * ld + b + 1] = m01;
+                M[(a + 1) * ld + b] = m10;
+                M[(a + 1) * ld + b + 1] = m11;
+            } else {
+                W[tw(idx)] = m00;
+                W[tw(idx + stride)] = m01;
+                W[tw(idx + 2 * stride)] = m10;
+                W[tw(idx + 3 * stride)] = m11;
+            }
         }
         gsync<GS>();
     }
 }
 
-// stage Q of the axis map: in [6^Q][4][4^(N-1-Q)] -> out [6^Q][6][4^(N-1-Q)]
+// stage Q of the axis map: in [6^Q][4][4^(N-1-Q)] -> out [6^Q][6][4^(N-1-Q)]; one thread per (prefix, suffix)
+// loads the four digits once and writes the six slots
 template <int N, int Q, int GS>
 __device__ __forceinline__ void axis_forward(const double* __restrict__ in, double* __restrict__ out, int lane) {
     constexpr int P4 = ipow(4, N - 1 - Q), PRE = ipow(6, Q);
-    for (int o = lane; o < PRE * 6 * P4; o += GS) {
-        const int post = o % P4, al = (o / P4) % 6, pre = o / (6 * P4);
-        const double x0 = in[(pre * 4) * P4 + post], xa = in[(pre * 4 + (al >> 1) + 1) * P4 + post];
-        out[o] = (al & 1) ? x0 - xa : x0 + xa;
+    for (int t = lane; t < PRE * P4; t += GS) {
+        const int post = t % P4, pre = t / P4;
+        const double* src = in + (pre * 4) * P4 + post;
+        double* dst = out + (pre * 6) * P4 + post;
+        const double x0 = src[0];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double xa = src[(a + 1) * P4];
+            dst[(2 * a) * P4] = x0 + xa;
+            dst[(2 * a + 1) * P4] = x0 - xa;
+        }
     }
     gsync<GS>();
 }
@@ -134,13 +212,15 @@ __device__ __forceinline__ void axis_forward(const double* __restrict__ in, doub
 template <int N, int Q, int GS>
 __device__ __forceinline__ void axis_adjoint(const double* __restrict__ in, double* __restrict__ out, int lane) {
     constexpr int P4 = ipow(4, N - 1 - Q), PRE = ipow(6, Q);
-    for (int o = lane; o < PRE * 4 * P4; o += GS) {
-        const int post = o % P4, dig = (o / P4) % 4, pre = o / (4 * P4);
+    for (int t = lane; t < PRE * P4; t += GS) {
+        const int post = t % P4, pre = t / P4;
         const double* src = in + (pre * 6) * P4 + post;
-        double v;
-        if (dig == 0) v = ((src[0] + src[P4]) + (src[2 * P4] + src[3 * P4])) + (src[4 * P4] + src[5 * P4]);
-        else v = src[(2 * (dig - 1)) * P4] - src[(2 * (dig - 1) + 1) * P4];
-        out[o] = v;
+        double* dst = out + (pre * 4) * P4 + post;
+        const double s0 = src[0], s1 = src[P4], s2 = src[2 * P4], s3 = src[3 * P4], s4 = src[4 * P4], s5 = src[5 * P4];
+        dst[0] = ((s0 + s1) + (s2 + s3)) + (s4 + s5);
+        dst[P4] = s0 - s1;
+        dst[2 * P4] = s2 - s3;
+        dst[3 * P4] = s4 - s5;
     }
     gsync<GS>();
 }
@@ -172,19 +252,22 @@ __device__ __forceinline__ void axis_last_fused(const double* __restrict__ in, d
                                                 const int* __restrict__ cnt, const double* __restrict__ epsp,
                                                 double inv_total, int lane) {
     constexpr int PRE = ipow(6, N - 1);
+    const double2* in2 = reinterpret_cast<const double2*>(in);  // buffers are 16-byte aligned, rows are 32 bytes
+    double2* out2 = reinterpret_cast<double2*>(out);
     for (int pre = lane; pre < PRE; pre += GS) {
-        const double x0 = in[pre * 4];
-        double u0 = 0.0;
+        const double2 lo = in2[pre * 2], hi = in2[pre * 2 + 1];
+        const double x0 = lo.x, xs[3] = {lo.y, hi.x, hi.y};
+        double u0 = 0.0, dif[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double xa = in[pre * 4 + a + 1];
             const int slot = pre * 6 + 2 * a;
-            const double wp = ((double)cnt[slot] * inv_total) * fast_recip((x0 + xa) + epsp[slot]);
-            const double wm = ((double)cnt[slot + 1] * inv_total) * fast_recip((x0 - xa) + epsp[slot + 1]);
+            const double wp = ((double)cnt[slot] * inv_total) * fast_recip((x0 + xs[a]) + epsp[slot]);
+            const double wm = ((double)cnt[slot + 1] * inv_total) * fast_recip((x0 - xs[a]) + epsp[slot + 1]);
             u0 += wp + wm;
-            out[pre * 4 + a + 1] = wp - wm;
+            dif[a] = wp - wm;
         }
-        out[pre * 4] = u0;
+        out2[pre * 2] = make_double2(u0, dif[0]);
+        out2[pre * 2 + 1] = make_double2(dif[1], dif[2]);
     }
     gsync<GS>();
 }
@@ -280,30 +363,13 @@ k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* 
         gsync<GS>();
         int it = 0;
         for (it = 1; it <= max_iter; ++it) {
-            // S_i = Tr(sigma_i rho)
-            for (int e = lane; e < D; e += GS) W[tw(interleave<N>(e / d, e % d))] = rho[(e / d) * ld + e % d];
-            gsync<GS>();
-            pauli_forward<N, GS>(W, lane);
-            for (int e = lane; e < D; e += GS) bufA[e] = W[tw(e)].x;
-            gsync<GS>();
+            // S_i = Tr(sigma_i rho), real parts straight into bufA
+            pauli_forward<N, GS>(rho, W, bufA, lane);
             double* q = axis_forward_all<N, GS>(bufA, bufB, lane);  // after N-1 stages: [6^(N-1)][4]
             double* u = q == bufA ? bufB : bufA;
             axis_last_fused<N, GS>(q, u, cnt, epsp, inv_total, lane);
             double* g = axis_adjoint_all<N, GS>(u, q, lane);  // Pauli coefficients of R
-            {  // g may live in the buffer W aliases: pass the coefficients through registers
-                constexpr int PER = (D + GS - 1) / GS;
-                double gv[PER];
-#pragma unroll
-                for (int j = 0; j < PER; ++j) gv[j] = (lane + j * GS < D) ? g[lane + j * GS] : 0.0;
-                gsync<GS>();
-#pragma unroll
-                for (int j = 0; j < PER; ++j)
-                    if (lane + j * GS < D) W[tw(lane + j * GS)] = make_double2(gv[j], 0.0);
-                gsync<GS>();
-            }
-            pauli_inverse<N, GS>(W, lane);
-            for (int e = lane; e < D; e += GS) Rm[(e / d) * ld + e % d] = W[tw(interleave<N>(e / d, e % d))];
-            gsync<GS>();
+            pauli_inverse<N, GS>(g, W, Rm, lane);
             cmatmul<N, GS>(W, Rm, rho, lane);   // W = R rho
             double2* T = reinterpret_cast<double2*>(bufA);  // 2*d*ld doubles fit in one contraction buffer (<= 6^N)
             cmatmul<N, GS>(T, W, Rm, lane);     // T = R rho R
