@@ -1,4 +1,4 @@
-// Register-resident batched Hermitian Jacobi + physical projection for d = 8 (n = 3):
+// Register-resident batched Hermitian Jacobi + physical projection for d = 8, 16 (n = 3, 4):
 // d LANES PER MATRIX, lane r owns row r of A and row r of the eigenvector matrix V.
 //
 // Replaces _make_feasible (quantpy/tomography/state.py:267-273) after the DMMA inversion for n = 3.  The
@@ -152,7 +152,7 @@ __device__ __forceinline__ void jacobi_round(RowState<d>& S, int gl, int gbase, 
 constexpr int kRowsThreads = 128;
 
 template <int d>
-__global__ void __launch_bounds__(kRowsThreads, 4)
+__global__ void __launch_bounds__(kRowsThreads, d == 8 ? 4 : 2)
 k_project_rows(int B, const double* __restrict__ h_in, double* __restrict__ rho) {
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int G = d, dd = d * d;
@@ -227,13 +227,15 @@ k_project_rows(int B, const double* __restrict__ h_in, double* __restrict__ rho)
     }
 }
 
-int launch_project_rows8(int B, const double* h_in, double* rho, cudaStream_t st) {
-    const long groups = kRowsThreads / 8;
+int launch_project_rows(int d, int B, const double* h_in, double* rho, cudaStream_t st) {
+    if (d != 8 && d != 16) return QPB_ERR_UNSUPPORTED;
+    const long groups = kRowsThreads / d;
     long blocks = ((long)B + groups - 1) / groups;
     const long cap = (long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    k_project_rows<8><<<(int)blocks, kRowsThreads, 0, st>>>(B, h_in, rho);
+    if (d == 8) k_project_rows<8><<<(int)blocks, kRowsThreads, 0, st>>>(B, h_in, rho);
+    else k_project_rows<16><<<(int)blocks, kRowsThreads, 0, st>>>(B, h_in, rho);
     QPB_LAUNCHED("k_project_rows");
     return QPB_OK;
 }

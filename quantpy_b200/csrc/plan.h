@@ -29,8 +29,8 @@ int launch_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts,
 // Register-resident variant for n <= 2 (lin_small.cu); QPB_ERR_UNSUPPORTED otherwise.
 int launch_lin_project_small(const qpb_state_plan* plan, int B, const int32_t* counts, int physical, double* rho,
                              cudaStream_t st);
-// Register-resident Jacobi + projection for d = 8 from packed-Hermitian inputs H [B][64] (jacobi_rows.cu)
-int launch_project_rows8(int B, const double* h_in, double* rho, cudaStream_t st);
+// Register-resident Jacobi + projection for d = 8, 16 from packed-Hermitian inputs H [B][d*d] (jacobi_rows.cu)
+int launch_project_rows(int d, int B, const double* h_in, double* rho, cudaStream_t st);
 int launch_mle_generic(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                        double tol, double* rho, int32_t* iters, cudaStream_t st);
 int launch_distance(int d, int B, const double* rho, const double* ref, int kind, double* dist, cudaStream_t st);

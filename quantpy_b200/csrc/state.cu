@@ -512,7 +512,10 @@ int launch_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts,
         if (rc != QPB_OK) return rc;
         h_in = H;
     }
-    if (h_in && plan->d == 8 && physical && !getenv("QPB_NO_ROW_JACOBI")) return launch_project_rows8(B, h_in, rho, st);
+    // d = 8, 16: one lane per matrix row, state in registers (measured per 1e5 / 1e4 matrices: 1.35 -> 0.95 ms against
+    // the shared-memory kernel at d = 8, 2.1 -> 1.4 ms against the warp-per-matrix kernel at d = 16)
+    if (h_in && physical && (plan->d == 8 || plan->d == 16) && !getenv("QPB_NO_ROW_JACOBI"))
+        return launch_project_rows(plan->d, B, h_in, rho, st);
     if (h_in && plan->d == 8 && !getenv("QPB_NO_PACKED_JACOBI")) {
         // 4 samples per warp, G = d = 8 lanes each (measured: 2.0 -> 1.35 ms per 1e5 matrices; at d = 16 two
         // matrices per warp were slower than one, 2.2 vs 1.9 ms per 1e4, so n = 4 keeps the warp-per-matrix kernel)
