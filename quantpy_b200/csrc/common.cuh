@@ -103,6 +103,19 @@ __device__ __forceinline__ double fast_recip(double y) {
     return fma(x, fma(e, e, e), x);
 }
 
+// counts / total for many counts of one sample: ONE IEEE reciprocal, then per count a product and a residual
+// correction (q = c r; q + r fma(-q, total, c)).  With r the correctly rounded reciprocal this is the correctly
+// rounded quotient (Markstein), i.e. the same bits as the ~35-instruction IEEE division it replaces -- 36 of
+// those per refilled lane were 12 % of the MLE kernel's stall samples (profiles/README_r1.md).
+struct FreqDiv {
+    double total, inv;
+    __device__ __forceinline__ explicit FreqDiv(double t) : total(t), inv(1.0 / t) {}
+    __device__ __forceinline__ double operator()(double c) const {
+        const double q = c * inv;
+        return fma(fma(-q, total, c), inv, q);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11).  key = 64-bit seed, counter = 128 bits.
 // ---------------------------------------------------------------------------------------------

@@ -87,13 +87,13 @@ k_lin_project_small(int K, int B, const double* __restrict__ LhT, const int32_t*
     const int32_t* c = counts + b * K;
     long long tot = 0;
     for (int k = 0; k < K; ++k) tot += c[k];
-    const double total = (double)tot;
+    const FreqDiv freq((double)tot);
     double h[D];
 #pragma unroll
     for (int e = 0; e < D; ++e) h[e] = 0.0;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-        const double f = (double)c[k] / total;  // state.py:193
+        const double f = freq((double)c[k]);  // state.py:193
         const double2* row = reinterpret_cast<const double2*>(tab + (size_t)k * D);
 #pragma unroll
         for (int e = 0; e < D / 2; ++e) {

@@ -128,7 +128,8 @@ k_mle_rrr_small(int K, int B, const double* __restrict__ Ar, const int32_t* __re
                     long long tot = 0;
                     for (int k = 0; k < K; ++k) tot += c[k];
                     const double total = (double)tot;
-                    for (int k = 0; k < K; ++k) fs[k * kSmallThreads + tid] = (double)c[k] / total;
+                    const FreqDiv freq(total);
+                    for (int k = 0; k < K; ++k) fs[k * kSmallThreads + tid] = freq((double)c[k]);
                     if (rho0) {
                         const double* r0 = rho0 + b * 2 * D;
 #pragma unroll
@@ -270,8 +271,9 @@ k_mle_rrr_const(const __grid_constant__ ConstTables<N, K> ct, int B, const int32
                         tot += cc[k];
                     }
                     const double total = (double)tot;
+                    const FreqDiv freq(total);
 #pragma unroll
-                    for (int k = 0; k < K; ++k) fs[k * kSmallThreads + tid] = (double)cc[k] / total;
+                    for (int k = 0; k < K; ++k) fs[k * kSmallThreads + tid] = freq((double)cc[k]);
                     if (rho0) {
                         const double2* r0 = reinterpret_cast<const double2*>(rho0) + b * D;
 #pragma unroll
@@ -546,10 +548,10 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
                     int tot = 0;
 #pragma unroll
                     for (int k = 0; k < 36; ++k) tot += cc[k];
-                    const double total = (double)tot;
+                    const FreqDiv freq((double)tot);
 #pragma unroll
                     for (int k = 0; k < 36; ++k)
-                        if (k < K) fs[pp.slot_of_col[k] * kPauliThreads + tid] = (double)cc[k] / total;
+                        if (k < K) fs[pp.slot_of_col[k] * kPauliThreads + tid] = freq((double)cc[k]);
                     if (rho0) {
                         const double2* r0 = reinterpret_cast<const double2*>(rho0) + b * D;
 #pragma unroll
