@@ -213,3 +213,21 @@ def test_all_gather_two_ranks_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_frequency_division_formula_is_correctly_rounded():
+    """csrc/common.cuh::FreqDiv turns counts/total into one reciprocal plus q = c*r; q + fma(-q, total, c)*r.
+    Emulated in exact rational arithmetic, the result has the bits of the IEEE quotient the reference computes
+    (state.py:193, 227) for every count of realistic shot totals."""
+    from fractions import Fraction as Fr
+
+    rng = np.random.default_rng(0)
+    totals = [3, 7, 1000, 9999, 10000, 30000, 90000, 12960000] + [int(t) for t in rng.integers(1, 10**7, 40)]
+    for t in totals:
+        inv = float(Fr(1) / t)
+        counts = range(t + 1) if t <= 1000 else [int(c) for c in rng.integers(0, t + 1, 400)]
+        for c in counts:
+            q = float(Fr(c) * Fr(inv))
+            res = float(Fr(c) - Fr(q) * t)           # fma(-q, total, c): exact product, one rounding
+            got = float(Fr(q) + Fr(res) * Fr(inv))   # fma(res, inv, q)
+            assert got == c / t, (c, t)
