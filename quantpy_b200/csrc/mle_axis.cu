@@ -26,16 +26,45 @@ struct Axis {
     static constexpr int D = d * d;          // 4^N
     static constexpr int K6 = ipow(6, N);    // canonical slots
     static constexpr int ld = d + 1;         // padded leading dimension of the complex matrices (bank conflicts)
+    // n = 4 keeps the complex matrices as separate re / im planes with a leading dimension of 20 doubles: the DMMA
+    // fragments of the two products (8 rows x 4 consecutive doubles per quarter-warp) then load in two wavefronts;
+    // n = 3 keeps interleaved complex numbers (its products stay on the FMA pipe).
+    static constexpr bool planar = (N == 4);
+    static constexpr int lp = 20;
+    static constexpr int mat = planar ? 2 * d * lp : 2 * d * ld;  // doubles per matrix
     // The two contraction buffers hold at most [6^(N-1)][4] reals: the last axis stage, the reciprocals and the
     // first adjoint stage are fused in registers, so the 6^N probabilities are never stored.  The transform /
     // product workspaces alias them (their lifetimes do not overlap), the counts stay int32.
     static constexpr int buf = ipow(6, N - 1) * 4;
-    static_assert(2 * d * ld <= buf, "matrix workspaces must fit in a contraction buffer");
-    // bytes of shared memory per sample: rho, R (complex d x ld), two buffers, counts
-    static constexpr size_t smem_bytes = sizeof(double) * (2 * 2 * d * ld + 2 * buf) + sizeof(int) * K6;
+    static_assert(mat <= buf, "matrix workspaces must fit in a contraction buffer");
+    // bytes of shared memory per sample: rho, R, two buffers, counts
+    static constexpr size_t smem_bytes = sizeof(double) * (2 * mat + 2 * buf) + sizeof(int) * K6;
     // resident CTAs per SM the launch bounds ask for (register cap), CTA size
     static constexpr int GS = (N == 4) ? 128 : 64;
     static constexpr int min_blocks = (N == 4) ? 7 : 16;
+};
+
+// d x d complex matrix in shared memory: interleaved (re, im) with leading dimension ld, or two planes
+template <int N>
+struct Mat {
+    double* p;
+    __device__ __forceinline__ double2 get(int a, int b) const {
+        if constexpr (Axis<N>::planar) {
+            return make_double2(p[a * Axis<N>::lp + b], p[Axis<N>::d * Axis<N>::lp + a * Axis<N>::lp + b]);
+        } else {
+            return reinterpret_cast<const double2*>(p)[a * Axis<N>::ld + b];
+        }
+    }
+    __device__ __forceinline__ void set(int a, int b, double2 z) const {
+        if constexpr (Axis<N>::planar) {
+            p[a * Axis<N>::lp + b] = z.x;
+            p[Axis<N>::d * Axis<N>::lp + a * Axis<N>::lp + b] = z.y;
+        } else {
+            reinterpret_cast<double2*>(p)[a * Axis<N>::ld + b] = z;
+        }
+    }
+    __device__ __forceinline__ const double* re() const { return p; }
+    __device__ __forceinline__ const double* im() const { return p + Axis<N>::d * Axis<N>::lp; }
 };
 
 // One sample is processed by a group of GS threads: a warp (GS = 32) or a whole CTA (GS = blockDim.x).
@@ -95,9 +124,9 @@ __device__ __forceinline__ void deinterleave(int e, int& a, int& b) {
 // M (row-major, leading dimension ld) directly, the middle stages run in place on the swizzled workspace W, the
 // last one writes only what is needed afterwards: the real parts, in natural order, to S.
 template <int N, int GS>
-__device__ __forceinline__ void pauli_forward(const double2* __restrict__ M, double2* __restrict__ W,
-                                              double* __restrict__ S, int lane) {
-    constexpr int D = Axis<N>::D, ld = Axis<N>::ld;
+__device__ __forceinline__ void pauli_forward(const Mat<N> M, double2* __restrict__ W, double* __restrict__ S,
+                                              int lane) {
+    constexpr int D = Axis<N>::D;
 #pragma unroll
     for (int q = 0; q < N; ++q) {
         const int stride = 1 << (2 * (N - 1 - q));
@@ -108,10 +137,10 @@ __device__ __forceinline__ void pauli_forward(const double2* __restrict__ M, dou
                 int al, bl;
                 deinterleave<N>(idx, al, bl);  // low bits of (row, column); the first qubit's digit selects the block
                 constexpr int H = 1 << (N - 1);
-                v0 = M[al * ld + bl];
-                v1 = M[al * ld + bl + H];
-                v2 = M[(al + H) * ld + bl];
-                v3 = M[(al + H) * ld + bl + H];
+                v0 = M.get(al, bl);
+                v1 = M.get(al, bl + H);
+                v2 = M.get(al + H, bl);
+                v3 = M.get(al + H, bl + H);
             } else {
                 v0 = W[tw(idx)];
                 v1 = W[tw(idx + stride)];
@@ -138,8 +167,8 @@ __device__ __forceinline__ void pauli_forward(const double2* __restrict__ M, dou
 // g may live in the buffer W aliases, so the first stage reads its quad into registers before anything is written.
 template <int N, int GS>
 __device__ __forceinline__ void pauli_inverse(const double* __restrict__ gcoef, double2* __restrict__ W,
-                                              double2* __restrict__ M, int lane) {
-    constexpr int D = Axis<N>::D, ld = Axis<N>::ld;
+                                              const Mat<N> M, int lane) {
+    constexpr int D = Axis<N>::D;
     static_assert(D / 4 <= GS, "one quad per thread in the first stage");
     {
         constexpr int stride = 1 << (2 * (N - 1));
@@ -173,10 +202,10 @@ __device__ __forceinline__ void pauli_inverse(const double* __restrict__ gcoef, 
             if (q == N - 1) {  // idx = 4 * (digits of the other qubits): the last qubit is the lowest bit of row and column
                 int a, b;
                 deinterleave<N>(idx, a, b);
-                M[a * ld + b] = m00;
-                M[a * ld + b + 1] = m01;
-                M[(a + 1) * ld + b] = m10;
-                M[(a + 1) * ld + b + 1] = m11;
+                M.set(a, b, m00);
+                M.set(a, b + 1, m01);
+                M.set(a + 1, b, m10);
+                M.set(a + 1, b + 1, m11);
             } else {
                 W[tw(idx)] = m00;
                 W[tw(idx + stride)] = m01;
@@ -272,46 +301,81 @@ __device__ __forceinline__ void axis_last_fused(const double* __restrict__ in, d
     gsync<GS>();
 }
 
-// C = X * Y for d x d complex matrices in shared memory (row-major, leading dimension ld = d + 1).
-// The kernel is bound by shared-memory wavefronts (ncu: 93 % of the LSU data pipe, 40 % of them from the Y loads of
-// this routine), so at n = 4 every lane owns a 2 x 4 register tile (rows a and a + d/2): 4 Y loads and 2 X loads
-// feed 8 complex multiply-adds.  Lanes of a quarter-warp share the column block (their Y address is one broadcast)
-// and differ in the row, whose stride of ld complex numbers keeps the X loads conflict-free.
+__device__ __forceinline__ void dmma_884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// C = X * Y for d x d complex matrices in shared memory, Y HERMITIAN (rho or R in both uses).
+//
+// n = 4: the kernel is bound by shared-memory wavefronts and the products were their largest source, so they run
+// on the FP64 tensor cores: warp w owns the 8 x 8 output tile (w / 2, w % 2) and per k-step of 4 issues four
+// mma.m8n8k4 (re += Xr Yr + Xi Yi^T..., see below) from four 64-bit fragment loads.  The B fragment is read
+// from the TRANSPOSED position with the imaginary part negated (Y[k][n] = conj(Y[n][k])), which gives it the
+// same conflict-free address pattern as the A fragment: rows 8 apart in tile, 4 consecutive doubles, lp = 20.
+//     C_re = Xr Br - Xi Bi,  C_im = Xr Bi + Xi Br,   Br[k][n] = Yr[n][k],  Bi[k][n] = -Yi[n][k]
+// n = 3: 2 x TJ register tiles on the FMA pipe out of interleaved storage (quarter-warps share the column block).
 template <int N, int GS>
-__device__ __forceinline__ void cmatmul(double2* __restrict__ C, const double2* __restrict__ X,
-                                        const double2* __restrict__ Y, int lane) {
-    constexpr int d = Axis<N>::d, ld = Axis<N>::ld;
-    // n = 4: 2 x 4 tiles (32 tasks, shared-memory bound); n = 3: 1 x 2 tiles (32 tasks, latency bound: keep lanes busy)
-    constexpr int TI = (d >= 16) ? 2 : 1, TJ = (d >= 16) ? 4 : 2, ROWS = d / TI;
-    constexpr int TASKS = ROWS * (d / TJ);
-    for (int t = lane; t < TASKS; t += GS) {
-        const int a = t % ROWS, b0 = (t / ROWS) * TJ;
-        double re[TI][TJ], im[TI][TJ];
+__device__ __forceinline__ void cmatmul(const Mat<N> C, const Mat<N> X, const Mat<N> Y, int lane) {
+    constexpr int d = Axis<N>::d;
+    if constexpr (Axis<N>::planar) {
+        constexpr int lp = Axis<N>::lp;
+        static_assert(d == 16 && GS == 128, "four warps, one 8 x 8 tile each");
+        const int w = lane >> 5, l = lane & 31;
+        const int ti = w >> 1, tj = w & 1, fr = l >> 2, fc = l & 3;
+        const double* xr = X.re() + (8 * ti + fr) * lp + fc;
+        const double* xi = X.im() + (8 * ti + fr) * lp + fc;
+        const double* yr = Y.re() + (8 * tj + fr) * lp + fc;
+        const double* yi = Y.im() + (8 * tj + fr) * lp + fc;
+        double cr0 = 0.0, cr1 = 0.0, ci0 = 0.0, ci1 = 0.0;
 #pragma unroll
-        for (int i = 0; i < TI; ++i)
+        for (int k0 = 0; k0 < d; k0 += 4) {
+            const double ar = xr[k0], ai = xi[k0], br = yr[k0], byi = yi[k0];
+            dmma_884(cr0, cr1, ar, br);    // Xr Br
+            dmma_884(cr0, cr1, ai, byi);   // -Xi Bi = Xi Yi^T
+            dmma_884(ci0, ci1, ai, br);    // Xi Br
+            dmma_884(ci0, ci1, ar, -byi);  // Xr Bi
+        }
+        double* cre = C.p + (8 * ti + fr) * lp + 8 * tj + 2 * fc;
+        *reinterpret_cast<double2*>(cre) = make_double2(cr0, cr1);
+        *reinterpret_cast<double2*>(cre + d * lp) = make_double2(ci0, ci1);
+    } else {
+        constexpr int ld = Axis<N>::ld;
+        const double2* Xp = reinterpret_cast<const double2*>(X.p);
+        const double2* Yp = reinterpret_cast<const double2*>(Y.p);
+        double2* Cp = reinterpret_cast<double2*>(C.p);
+        constexpr int TI = 1, TJ = 2, ROWS = d / TI;
+        constexpr int TASKS = ROWS * (d / TJ);
+        for (int t = lane; t < TASKS; t += GS) {
+            const int a = t % ROWS, b0 = (t / ROWS) * TJ;
+            double re[TI][TJ], im[TI][TJ];
 #pragma unroll
-            for (int j = 0; j < TJ; ++j) re[i][j] = im[i][j] = 0.0;
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) re[i][j] = im[i][j] = 0.0;
 #pragma unroll 2
-        for (int c = 0; c < d; ++c) {
-            double2 x[TI];
+            for (int c = 0; c < d; ++c) {
+                double2 x[TI];
 #pragma unroll
-            for (int i = 0; i < TI; ++i) x[i] = X[(a + i * ROWS) * ld + c];
+                for (int i = 0; i < TI; ++i) x[i] = Xp[(a + i * ROWS) * ld + c];
 #pragma unroll
-            for (int j = 0; j < TJ; ++j) {
-                const double2 y = Y[c * ld + b0 + j];
+                for (int j = 0; j < TJ; ++j) {
+                    const double2 y = Yp[c * ld + b0 + j];
 #pragma unroll
-                for (int i = 0; i < TI; ++i) {
-                    re[i][j] = fma(x[i].x, y.x, re[i][j]);
-                    re[i][j] = fma(-x[i].y, y.y, re[i][j]);
-                    im[i][j] = fma(x[i].x, y.y, im[i][j]);
-                    im[i][j] = fma(x[i].y, y.x, im[i][j]);
+                    for (int i = 0; i < TI; ++i) {
+                        re[i][j] = fma(x[i].x, y.x, re[i][j]);
+                        re[i][j] = fma(-x[i].y, y.y, re[i][j]);
+                        im[i][j] = fma(x[i].x, y.y, im[i][j]);
+                        im[i][j] = fma(x[i].y, y.x, im[i][j]);
+                    }
                 }
             }
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) Cp[(a + i * ROWS) * ld + b0 + j] = make_double2(re[i][j], im[i][j]);
         }
-#pragma unroll
-        for (int i = 0; i < TI; ++i)
-#pragma unroll
-            for (int j = 0; j < TJ; ++j) C[(a + i * ROWS) * ld + b0 + j] = make_double2(re[i][j], im[i][j]);
     }
     gsync<GS>();
 }
@@ -321,18 +385,18 @@ __global__ void __launch_bounds__(GS, Axis<N>::min_blocks)
 k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* __restrict__ epsp,
                const int32_t* __restrict__ counts, const double* __restrict__ rho0, int max_iter, double tol,
                double* __restrict__ rho_out, int32_t* __restrict__ iters, unsigned int* __restrict__ queue) {
-    constexpr int d = Axis<N>::d, D = Axis<N>::D, K6 = Axis<N>::K6, ld = Axis<N>::ld;
+    constexpr int d = Axis<N>::d, D = Axis<N>::D, K6 = Axis<N>::K6, MAT = Axis<N>::mat;
     extern __shared__ __align__(16) double smd[];
     __shared__ double red[32];
     __shared__ unsigned int next_sample;
     const int lane = threadIdx.x;  // index within the group (= CTA)
     constexpr int BUF = Axis<N>::buf;
-    double2* rho = reinterpret_cast<double2*>(smd);    // [d][ld]
-    double2* Rm = rho + d * ld;                        // [d][ld]
-    double* bufA = reinterpret_cast<double*>(Rm + d * ld);
+    const Mat<N> rho{smd}, Rm{smd + MAT};
+    double* bufA = smd + 2 * MAT;
     double* bufB = bufA + BUF;
     int* cnt = reinterpret_cast<int*>(bufB + BUF);     // counts in canonical slot order
-    double2* W = reinterpret_cast<double2*>(bufB);     // transform workspace (dense D) / product (padded): aliases bufB
+    double2* W = reinterpret_cast<double2*>(bufB);     // transform workspace (dense D, swizzled): aliases bufB
+    const Mat<N> P1{bufB}, T{bufA};                    // R rho and R rho R: alias the contraction buffers
 
     for (;;) {
         __syncthreads();
@@ -354,11 +418,10 @@ k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* 
             for (int e = lane; e < D; e += GS) {  // Hermitian part of the start, as the packed kernels take it
                 const int a = e / d, bb = e % d;
                 const double2 z = r0[e], zt = r0[bb * d + a];
-                rho[a * ld + bb] = (a == bb) ? make_double2(z.x, 0.0) : (a < bb ? z : make_double2(zt.x, -zt.y));
+                rho.set(a, bb, (a == bb) ? make_double2(z.x, 0.0) : (a < bb ? z : make_double2(zt.x, -zt.y)));
             }
         } else {
-            for (int e = lane; e < D; e += GS)
-                rho[(e / d) * ld + e % d] = make_double2((e / d == e % d) ? 1.0 / d : 0.0, 0.0);
+            for (int e = lane; e < D; e += GS) rho.set(e / d, e % d, make_double2((e / d == e % d) ? 1.0 / d : 0.0, 0.0));
         }
         gsync<GS>();
         int it = 0;
@@ -370,12 +433,11 @@ k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* 
             axis_last_fused<N, GS>(q, u, cnt, epsp, inv_total, lane);
             double* g = axis_adjoint_all<N, GS>(u, q, lane);  // Pauli coefficients of R
             pauli_inverse<N, GS>(g, W, Rm, lane);
-            cmatmul<N, GS>(W, Rm, rho, lane);   // W = R rho
-            double2* T = reinterpret_cast<double2*>(bufA);  // 2*d*ld doubles fit in one contraction buffer (<= 6^N)
-            cmatmul<N, GS>(T, W, Rm, lane);     // T = R rho R
+            cmatmul<N, GS>(P1, Rm, rho, lane);  // P1 = R rho
+            cmatmul<N, GS>(T, P1, Rm, lane);    // T = R rho R
             // Hermitise, normalise, step norm
             double tr = 0.0;
-            for (int a = lane; a < d; a += GS) tr += T[a * ld + a].x;
+            for (int a = lane; a < d; a += GS) tr += T.get(a, a).x;
             tr = gsum<GS>(tr, red, lane);
             const double inv = 1.0 / tr;
             double del = 0.0;
@@ -383,25 +445,25 @@ k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* 
                 const int a = e / d, bb = e % d;
                 double2 v;
                 if (a == bb) {
-                    v = make_double2(T[a * ld + a].x * inv, 0.0);
+                    v = make_double2(T.get(a, a).x * inv, 0.0);
                 } else {
-                    const double2 z = T[a * ld + bb], zt = T[bb * ld + a];
+                    const double2 z = T.get(a, bb), zt = T.get(bb, a);
                     v = make_double2(0.5 * (z.x + zt.x) * inv, 0.5 * (z.y - zt.y) * inv);
                 }
-                const double2 old = rho[a * ld + bb];
+                const double2 old = rho.get(a, bb);
                 const double dr = v.x - old.x, di = v.y - old.y;
                 del += dr * dr + di * di;
-                W[a * ld + bb] = v;
+                P1.set(a, bb, v);
             }
             del = sqrt(gsum<GS>(del, red, lane));
             gsync<GS>();
-            for (int e = lane; e < D; e += GS) rho[(e / d) * ld + e % d] = W[(e / d) * ld + e % d];
+            for (int e = lane; e < D; e += GS) rho.set(e / d, e % d, P1.get(e / d, e % d));
             gsync<GS>();
             if (del < tol) break;
         }
         if (it > max_iter) it = max_iter;
         double2* out = reinterpret_cast<double2*>(rho_out) + (size_t)b * D;
-        for (int e = lane; e < D; e += GS) out[e] = rho[(e / d) * ld + e % d];
+        for (int e = lane; e < D; e += GS) out[e] = rho.get(e / d, e % d);
         if (iters && lane == 0) iters[b] = it;
     }
 }
