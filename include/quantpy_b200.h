@@ -170,6 +170,11 @@ QPB_API int qpb_mhmc_state(const qpb_state_plan* plan, int C, int n_samples, int
                    const double* uniforms, uint64_t seed, uint64_t chain_offset, double* samples, int32_t* accepted,
                    double* x_final, void* stream);
 
+/* ---- quantile step ----------------------------------------------------------------------------
+ * out = sorted(in) ascending, n float64 keys, in != out (`dist.sort()`, interval.py:610 / 683).  Keys only: the
+ * quantile function needs the order statistics, not the permutation.                                   */
+QPB_API int qpb_sort_f64(long long n, const double* in, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

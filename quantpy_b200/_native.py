@@ -50,6 +50,7 @@ SIGNATURES = {
     "qpb_polytope_coverage": (_int, [_int, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _int, _vp, _vp, _vp]),
     "qpb_polytope_confidence": (_int, [_int, _int, _int, _vp, _vp, _int, _vp, _vp, _vp]),
     "qpb_l2_moments": (_int, [_int, _int, _int, _vp, _vp, _dbl, _vp, _vp, _vp]),
+    "qpb_sort_f64": (_int, [ctypes.c_longlong, _vp, _vp, _vp]),
     "qpb_mhmc_state": (_int, [_vp, _int, _int, _int, _int, _dbl, _vp, _int, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp,
                               _vp]),
     "qpb_process_plan_create": (_int, [ctypes.POINTER(_vp), _int, _int, _int, _vp, _vp]),

@@ -170,6 +170,16 @@ class StatePlan:
         return bufs
 
 
+def sort_f64(values):
+    """Ascending sort of a 1-D float64 device tensor (keys only) -> new device tensor."""
+    torch = nt.torch_cuda()
+    lib = nt.load_library()
+    v = values.contiguous()
+    out = torch.empty_like(v)
+    nt.check(lib.qpb_sort_f64(int(v.numel()), nt.ptr(v), nt.ptr(out), nt.stream_ptr()))
+    return out
+
+
 def cholesky_vector(matrix):
     """Packed Cholesky parametrisation of a positive-definite matrix (quantpy/routines.py:84-91): the diagonal of
     the lower factor, then the real and the imaginary parts of its strict lower triangle (np.tril_indices order).

@@ -69,6 +69,16 @@ TRAFFIC = {"d2h": 0, "h2d": 0}
 _PINNED = {}
 
 
+def _pinned(dtype, numel):
+    """Cached page-locked staging buffer (grow-only per dtype)."""
+    import torch
+
+    buf = _PINNED.get(dtype)
+    if buf is None or buf.numel() < numel:
+        buf = _PINNED[dtype] = torch.empty((max(int(numel), 4096),), dtype=dtype, pin_memory=True)
+    return buf[:numel]
+
+
 def to_host_pinned(tensor):
     """Device tensor -> NumPy array through a cached page-locked staging buffer (pageable copies of a few MB run
     at a fraction of the PCIe rate and dominated the multi-GPU end-to-end time)."""
@@ -76,12 +86,7 @@ def to_host_pinned(tensor):
 
     if not tensor.is_cuda:
         return tensor.numpy().copy()
-    key = (tensor.dtype, tensor.numel())
-    buf = _PINNED.get(key)
-    if buf is None:
-        if len(_PINNED) > 8:
-            _PINNED.clear()
-        buf = _PINNED[key] = torch.empty(tensor.shape, dtype=tensor.dtype, pin_memory=True)
+    buf = _pinned(tensor.dtype, tensor.numel()).view(tensor.shape)
     buf.copy_(tensor, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     TRAFFIC["d2h"] += tensor.numel() * tensor.element_size()
@@ -136,10 +141,17 @@ class QuantileFunction:
         if self._y is None:
             import torch
 
-            idx = torch.from_numpy(np.concatenate([lo.reshape(-1), lo.reshape(-1) + 1])).to(self._dev.device)
-            pair = self._dev[idx].cpu().numpy()
-            TRAFFIC["h2d"] += idx.numel() * 8
-            TRAFFIC["d2h"] += pair.size * 8
+            m = 2 * lo.size
+            stage = _pinned(torch.int64, m)  # both copies go through page-locked staging: no pageable round trips
+            stage.numpy()[: lo.size] = lo.reshape(-1)
+            stage.numpy()[lo.size:] = lo.reshape(-1) + 1
+            idx = stage.to(self._dev.device, non_blocking=True)
+            out = _pinned(torch.float64, m)
+            out.copy_(self._dev[idx], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            pair = out.numpy().copy()
+            TRAFFIC["h2d"] += m * 8
+            TRAFFIC["d2h"] += m * 8
             y_lo, y_hi = pair[: lo.size].reshape(lo.shape), pair[lo.size:].reshape(lo.shape)
         else:
             y_lo, y_hi = self._y[lo], self._y[lo + 1]
@@ -150,7 +162,11 @@ def quantile_function(dist_values, presorted=False):
     """Sorted distances -> interpolant of (linspace(0, 1, N), dist) as quantpy/tomography/interval.py:610-612.
     A CUDA tensor stays on the device (sorted there if needed)."""
     if hasattr(dist_values, "is_cuda") and dist_values.is_cuda:
-        return QuantileFunction(dist_values if presorted else dist_values.sort().values)
+        if not presorted:
+            from . import engine
+
+            dist_values = engine.sort_f64(dist_values)
+        return QuantileFunction(dist_values)
     ordered = np.asarray(dist_values, dtype=np.float64)
     if not presorted:
         ordered = np.sort(ordered)

@@ -59,7 +59,7 @@ class ConfidenceInterval(ABC):
         """All-gather the per-rank distances, keep them (sorted) and build the quantile function."""
         full = parallel.all_gather_concat(local_dist, n_points)
         # sorted on the device and left there: the quantile function fetches what a call needs, `dist` the rest
-        self.cl_to_dist = parallel.quantile_function(full.sort().values, presorted=True)
+        self.cl_to_dist = parallel.quantile_function(full)
 
     @property
     def dist(self):
