@@ -75,8 +75,8 @@ def parse():
 
 def workload_config(args, world):
     return {
-        "workload": f"BASELINE configs[1]: {args.n_qubits}-qubit Haar-random state (seed {args.state_seed}{", rank %d" % args.state_rank if args.state_rank else ""}), "
-                    f"{6**args.n_qubits if args.povm == 'proj' else '?'}-outcome Pauli '{args.povm}' POVM, "
+        "workload": f"BASELINE configs[{ {1: 0, 2: 1, 3: 2, 4: 3}.get(args.n_qubits, 1) }]: {args.n_qubits}-qubit Haar-random state (seed {args.state_seed}{", rank %d" % args.state_rank if args.state_rank else ""}), "
+                    f"{6**args.n_qubits if args.povm == 'proj' else str(3**args.n_qubits) + 'x' + str(2**args.n_qubits) if args.povm == 'proj-set' else '?'}-outcome Pauli '{args.povm}' POVM, "
                     f"{args.shots} shots, {args.resamples} {args.method.upper()} bootstrap resamples per GPU per step",
         "n_qubits": args.n_qubits, "povm": args.povm, "shots": args.shots,
         "resamples_per_gpu": args.resamples, "global_resamples": args.resamples * world,
