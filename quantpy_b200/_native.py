@@ -86,13 +86,20 @@ def load_library():
     return _lib
 
 
-def torch_cuda():
-    """Return the torch module after checking that a CUDA device is usable."""
-    import torch
+_torch = None
 
-    if not torch.cuda.is_available():
-        raise NativeError("quantpy_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
-    return torch
+
+def torch_cuda():
+    """Return the torch module after checking that a CUDA device is usable (checked once: the probe costs a few
+    microseconds and every entry point of the package passes through here)."""
+    global _torch
+    if _torch is None:
+        import torch
+
+        if not torch.cuda.is_available():
+            raise NativeError("quantpy_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        _torch = torch
+    return _torch
 
 
 def check(rc):
