@@ -231,3 +231,44 @@ def test_frequency_division_formula_is_correctly_rounded():
             res = float(Fr(c) - Fr(q) * t)           # fma(-q, total, c): exact product, one rounding
             got = float(Fr(q) + Fr(res) * Fr(inv))   # fma(res, inv, q)
             assert got == c / t, (c, t)
+
+
+def test_quantile_function_equals_scipy_interp1d():
+    """parallel.QuantileFunction is the object the reference builds with interp1d(linspace(0, 1, N), sorted dist)
+    (interval.py:610-612): same values on random grids, same `.x` / `.y`, same ValueError outside [0, 1]."""
+    from scipy.interpolate import interp1d
+
+    from quantpy_b200 import parallel
+
+    rng = np.random.default_rng(3)
+    for n in (2, 3, 17, 1000):
+        dist = np.sort(rng.random(n))
+        ref = interp1d(np.linspace(0, 1, n), dist)
+        q = parallel.quantile_function(dist[::-1].copy())
+        levels = np.concatenate([[0.0, 1.0], rng.random(200), np.linspace(0, 1, n)])
+        assert np.allclose(q(levels), ref(levels), rtol=0, atol=1e-15)
+        assert np.array_equal(q.x, ref.x) and np.array_equal(q.y, ref.y)
+        assert q(np.array([[0.25, 0.5]])).shape == (1, 2)
+        for bad in (-1e-9, 1 + 1e-9):
+            with pytest.raises(ValueError):
+                q(bad)
+            with pytest.raises(ValueError):
+                ref(bad)
+
+
+def test_shard_bounds_partition_any_range():
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from quantpy_b200 import parallel
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 10**6), st.integers(1, 64))
+    def check(n, world):
+        edges = [parallel.shard_bounds(n, r, world) for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+        sizes = [hi - lo for lo, hi in edges]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+    check()
