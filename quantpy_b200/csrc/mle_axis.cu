@@ -440,24 +440,28 @@ k_mle_rrr_axis(int K, int B, const int* __restrict__ slot_of_col, const double* 
             for (int a = lane; a < d; a += GS) tr += T.get(a, a).x;
             tr = gsum<GS>(tr, red, lane);
             const double inv = 1.0 / tr;
+            // one thread per element of the upper triangle: reads T(a,b), T(b,a) and the old rho(a,b), writes the new
+            // rho(a,b) and its conjugate in place (nobody else touches the pair), counts the pair's step norm twice
             double del = 0.0;
             for (int e = lane; e < D; e += GS) {
                 const int a = e / d, bb = e % d;
-                double2 v;
+                if (a > bb) continue;
+                const double2 old = rho.get(a, bb);
                 if (a == bb) {
-                    v = make_double2(T.get(a, a).x * inv, 0.0);
+                    const double v = T.get(a, a).x * inv;
+                    const double dr = v - old.x;
+                    del += dr * dr;
+                    rho.set(a, a, make_double2(v, 0.0));
                 } else {
                     const double2 z = T.get(a, bb), zt = T.get(bb, a);
-                    v = make_double2(0.5 * (z.x + zt.x) * inv, 0.5 * (z.y - zt.y) * inv);
+                    const double2 v = make_double2(0.5 * (z.x + zt.x) * inv, 0.5 * (z.y - zt.y) * inv);
+                    const double dr = v.x - old.x, di = v.y - old.y;
+                    del += 2.0 * (dr * dr + di * di);
+                    rho.set(a, bb, v);
+                    rho.set(bb, a, make_double2(v.x, -v.y));
                 }
-                const double2 old = rho.get(a, bb);
-                const double dr = v.x - old.x, di = v.y - old.y;
-                del += dr * dr + di * di;
-                P1.set(a, bb, v);
             }
             del = sqrt(gsum<GS>(del, red, lane));
-            gsync<GS>();
-            for (int e = lane; e < D; e += GS) rho.set(e / d, e % d, P1.get(e / d, e % d));
             gsync<GS>();
             if (del < tol) break;
         }
