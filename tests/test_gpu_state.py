@@ -196,6 +196,33 @@ def test_lin_matches_oracle_on_gpu_counts(qp, n, B):
     assert np.linalg.eigvalsh(got).min() > 0
 
 
+@pytest.mark.parametrize("n", [3, 4])
+def test_projection_on_degenerate_and_extreme_spectra(qp, n):
+    """The register-resident Jacobi (one lane per matrix row) on inputs that stress it: a maximally degenerate
+    spectrum (uniform counts -> identity / d, already diagonal), counts of a pure product state (rank 1, most
+    eigenvalues clipped at 1e-15), and a batch size that leaves lane groups of the last warp without a matrix."""
+    povm = qp.generate_measurement_matrix("proj", n)
+    K = povm.shape[1]
+    tmg = qp.StateTomograph(qp.Qobj(np.eye(2**n) / 2**n))
+    tmg.povm_matrix = povm
+    tmg.n_measurements = np.ones(1) * 6**n * 10
+    uniform = np.full((1, K), 10, dtype=np.int64)
+    ket = np.zeros(2**n); ket[0] = 1.0
+    pure = np.outer(ket, ket)
+    p = np.clip(povm[0] @ qp.Qobj(pure).bloch * 2**n, 0, 1)
+    exact = np.rint(p * 6**n * 10).astype(np.int64)[None]
+    exact[0, np.argmax(exact[0])] += 6**n * 10 - exact.sum()
+    rng = np.random.default_rng(n)
+    noisy = rng.multinomial(6**n * 10, p, size=3)
+    counts = np.concatenate([uniform, exact, noisy])  # B = 5
+    got = tmg.point_estimate_batch(counts[:, None, :], "lin")
+    want = ostate.lin_estimate(counts[:, None, :], povm, tmg.n_measurements)
+    assert fro(got, want).max() < 1e-10
+    assert fro(got[0], np.eye(2**n) / 2**n) < 1e-12
+    assert np.abs(np.trace(got, axis1=1, axis2=2) - 1).max() < 1e-12
+    assert np.linalg.eigvalsh(got).min() > -1e-15
+
+
 # ----------------------------------------------------------------------------- maximum likelihood
 
 @pytest.mark.parametrize("case", ["state_c1", "state_c1_pure", "state_c2", "state_c2_set", "state_c2_rank1",
