@@ -70,6 +70,16 @@ int qpb_bootstrap_state(const qpb_state_plan* plan, int B, int P, int O, const d
             if (rc != QPB_OK) return rc;
             start = buf0;
         }
+        if (dist_kind == QPB_DIST_HS && max_iter > 0 && mle_variant(plan) == QPB_MLE_PAULI2) {
+            // two-qubit Pauli-axis POVMs: the MLE kernel writes the distances itself; the states are stored only if
+            // the caller asked for them
+            bool done = false;
+            rc = launch_mle_small(plan, B, counts_out, start, max_iter, tol, final_rho, iters_out, st, ref, dist, &done,
+                                  rho_out ? 1 : 0);
+            if (rc != QPB_OK) return rc;
+            if (done) return QPB_OK;
+            return launch_distance(plan->d, B, final_rho, ref, dist_kind, dist, st);
+        }
         rc = qpb_mle_rrr(plan, B, counts_out, start, max_iter, tol, final_rho, iters_out, stream);
         if (rc != QPB_OK) return rc;
     }

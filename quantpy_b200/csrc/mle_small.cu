@@ -501,7 +501,8 @@ template <bool UNIFORM_GUARD>  // all used slots share one 1e-10/c: fold it into
 __global__ void __launch_bounds__(kPauliThreads, 1)
 k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* __restrict__ counts,
                  const double* __restrict__ rho0, int max_iter, double tol, double* __restrict__ rho,
-                 int32_t* __restrict__ iters, unsigned int* __restrict__ queue, int merge_tail) {
+                 int32_t* __restrict__ iters, unsigned int* __restrict__ queue, int merge_tail,
+                 const double* __restrict__ hs_ref, double* __restrict__ hs_dist) {
     constexpr int d = 4, D = 16;
     extern __shared__ __align__(16) double sm[];
     double* fs = sm;  // [36][kPauliThreads], column = owning thread at load time
@@ -698,16 +699,35 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* _
             }
         }
         if (finished) {
-            double2* out = reinterpret_cast<double2*>(rho) + b * D;
+            if (rho) {
+                double2* out = reinterpret_cast<double2*>(rho) + b * D;
 #pragma unroll
-            for (int a = 0; a < d; ++a)
+                for (int a = 0; a < d; ++a)
 #pragma unroll
-                for (int bb = 0; bb < d; ++bb) {
-                    double2 z;
-                    z.x = Packed<d>::re(h, a, bb);
-                    z.y = Packed<d>::im(h, a, bb);
-                    out[a * d + bb] = z;
-                }
+                    for (int bb = 0; bb < d; ++bb) {
+                        double2 z;
+                        z.x = Packed<d>::re(h, a, bb);
+                        z.y = Packed<d>::im(h, a, bb);
+                        out[a * d + bb] = z;
+                    }
+            }
+            if (hs_dist) {
+                // hs_dst(rho, ref) = sqrt(|Tr (rho - ref)^2|) / sqrt 2, no conjugate (quantpy/geometry.py:5-17); same
+                // formula as k_distance, evaluated here so that the bootstrap needs neither the state nor a fourth kernel
+                double sr = 0.0, si = 0.0;
+#pragma unroll
+                for (int a = 0; a < d; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < d; ++bb) {
+                        const double ur = Packed<d>::re(h, a, bb) - __ldg(hs_ref + 2 * (a * d + bb));
+                        const double ui = Packed<d>::im(h, a, bb) - __ldg(hs_ref + 2 * (a * d + bb) + 1);
+                        const double vr = Packed<d>::re(h, bb, a) - __ldg(hs_ref + 2 * (bb * d + a));
+                        const double vi = Packed<d>::im(h, bb, a) - __ldg(hs_ref + 2 * (bb * d + a) + 1);
+                        sr += ur * vr - ui * vi;
+                        si += ur * vi + ui * vr;
+                    }
+                hs_dist[b] = sqrt(sqrt(sr * sr + si * si)) / sqrt(2.0);
+            }
             if (iters) iters[b] = it;
             b = -1;
         }
@@ -774,7 +794,9 @@ int mle_variant(const qpb_state_plan* plan) {
 }
 
 int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
-                     double tol, double* rho, int32_t* iters, cudaStream_t st) {
+                     double tol, double* rho, int32_t* iters, cudaStream_t st, const double* hs_ref, double* hs_dist,
+                     bool* hs_done, int hs_store_rho) {
+    if (hs_done) *hs_done = false;
     if (plan->n > 2) return QPB_ERR_UNSUPPORTED;
     const size_t smem = sizeof(double) * ((size_t)plan->K * plan->D + (size_t)plan->K * kSmallThreads);
     if (smem > 200 * 1024) return QPB_ERR_UNSUPPORTED;
@@ -791,8 +813,13 @@ int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, c
             const long need = ((long)B + kPauliThreads - 1) / kPauliThreads;
             if (blocks > need) blocks = need;
             const int merge = getenv("QPB_NO_TAIL_MERGE") ? 0 : 1;
-            pk<<<(int)blocks, kPauliThreads, smem, st>>>(pp, B, counts, rho0, max_iter, tol, rho, iters, queue, merge);
+            const bool fuse = hs_ref && hs_dist && hs_done && !getenv("QPB_NO_HS_FUSION");
+            // with the distance fused and no caller for the states, they are not written at all
+            double* rho_dst = (fuse && hs_store_rho == 0) ? nullptr : rho;
+            pk<<<(int)blocks, kPauliThreads, smem, st>>>(pp, B, counts, rho0, max_iter, tol, rho_dst, iters, queue, merge,
+                                                        fuse ? hs_ref : nullptr, fuse ? hs_dist : nullptr);
             QPB_LAUNCHED("k_mle_rrr_pauli2");
+            if (fuse) *hs_done = true;
             return QPB_OK;
         }
     }

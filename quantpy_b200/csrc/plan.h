@@ -36,8 +36,12 @@ int launch_mle_generic(const qpb_state_plan* plan, int B, const int32_t* counts,
 int launch_distance(int d, int B, const double* rho, const double* ref, int kind, double* dist, cudaStream_t st);
 // Specialised register-resident kernels for n <= 2 (mle_small.cu).  Returns QPB_ERR_UNSUPPORTED when
 // the shape has no specialisation, in which case the caller uses the generic kernel.
+// hs_ref / hs_dist / hs_done (optional): the kernel may also write the Hilbert-Schmidt distance of every result to
+// the complex d x d centre state hs_ref and then sets *hs_done; if it does and hs_store_rho == 0 the states are
+// not written (rho must still be a valid buffer: kernels without the fusion use it).
 int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
-                     double tol, double* rho, int32_t* iters, cudaStream_t st);
+                     double tol, double* rho, int32_t* iters, cudaStream_t st, const double* hs_ref = nullptr,
+                     double* hs_dist = nullptr, bool* hs_done = nullptr, int hs_store_rho = 1);
 
 int mle_variant(const qpb_state_plan* plan);
 // C [M][N] = (counts [M][Ktot] normalised per group of G columns) * T [Ktot][N] on DMMA (gemm_dmma.cu)
