@@ -88,6 +88,58 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
+class NvmlSampler:
+    """SM clock, power and throttle reasons polled through NVML every 2 ms from a thread of this process: the timed
+    region of the default run is ~20 ms, too short for nvidia-smi's 100 ms loop to see more than once."""
+
+    def __init__(self, index):
+        import pynvml
+
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.sm, self.power, self.mask = [], [], 0
+        self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        self._stop = threading.Event()
+        self.thread = None
+
+    def start(self):
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm),
+                "reasons": sorted(n for n, bit in names if self.mask & bit), "source": "nvml, 2 ms poll"}
+
+
+def clock_sampler(index):
+    """NVML in-process when available, else an nvidia-smi loop."""
+    try:
+        return NvmlSampler(index)
+    except Exception:
+        return ClockSampler(index)
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -296,7 +348,7 @@ def run_ours(args, rank, local_rank, world):
     for i in range(args.warmup):
         step(i)
     barrier()
-    clocks = ClockSampler(local_rank)
+    clocks = clock_sampler(local_rank)
     if rank == 0:
         clocks.start()
     lib.qpb_reset_launch_count()
