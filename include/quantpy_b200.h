@@ -41,6 +41,31 @@ enum { QPB_INIT_LIN = 0, QPB_INIT_MIXED = 1 };                       /* state.py
 QPB_API int qpb_abi_version(void);
 QPB_API const char* qpb_last_error(void);
 /* Number of kernels launched by this library since load / since the last reset (bench bookkeeping). */
+/* Kernel-selection toggles for tests and profiling (never needed in production).  Each is initialised ONCE, when
+ * the library is loaded, from the environment variable of the same name with the prefix QPB_ (e.g.
+ * QPB_NO_TAIL_MERGE=1); qpb_set_option changes it afterwards.  No launch path reads the environment. */
+enum {
+    QPB_OPT_NO_TAIL_MERGE = 0,   /* pauli2 MLE: no hand-over of long-running samples to warp-per-sample workers */
+    QPB_OPT_NO_HS_FUSION = 1,    /* bootstrap: Hilbert-Schmidt distance by k_distance instead of the MLE write-back */
+    QPB_OPT_NO_PAULI_KERNEL = 2,
+    QPB_OPT_NO_CONST_KERNEL = 3,
+    QPB_OPT_NO_AXIS_KERNEL = 4,
+    QPB_OPT_NO_DMMA_GEMM = 5,
+    QPB_OPT_NO_ROW_JACOBI = 6,
+    QPB_OPT_NO_PACKED_JACOBI = 7,
+    QPB_OPT_NO_LIN_SMALL = 8,
+    QPB_OPT_SAMPLER = 9,         /* 0 auto | 1 alias | 2 conditional binomial (env: "alias" / "binomial") */
+    QPB_OPT_MLE_BLOCKS_PER_SM = 10,
+    QPB_OPT_MLE_LANES = 11,      /* pauli2 MLE: 0 auto | 1 thread per sample only | 32 warp per sample only */
+    QPB_OPT_NO_TILED_MLE = 12,   /* general-POVM MLE at n >= 3: warp-per-sample kernel instead of the DMMA-tiled one */
+    QPB_OPT_MLE_PARK_AGE = 13,   /* pauli2 MLE tuning: iteration count at which a sample moves to a warp-per-sample worker (0 = default) */
+    QPB_OPT_MLE_PARK_LIVE = 14,  /* pauli2 MLE tuning: a drained warp with at most this many live samples hands them all over (0 = default) */
+    QPB_OPT_MLE_W_WARPS = 15,    /* pauli2 MLE tuning: warp-per-sample workers per CTA from the start (0 = default, -1 = none) */
+    QPB_OPT_MLE_PARK_PLATEAU = 16, /* pauli2 MLE tuning: first iteration count at which a non-decreasing step norm hands a sample over (0 = default, -1 = never) */
+    QPB_OPT_COUNT_ = 17
+};
+QPB_API int qpb_set_option(int which, int value);
+QPB_API int qpb_get_option(int which);
 QPB_API int64_t qpb_launch_count(void);
 QPB_API void qpb_reset_launch_count(void);
 

@@ -33,6 +33,8 @@ SIGNATURES = {
     "qpb_last_error": (ctypes.c_char_p, []),
     "qpb_launch_count": (ctypes.c_int64, []),
     "qpb_reset_launch_count": (None, []),
+    "qpb_set_option": (_int, [_int, _int]),
+    "qpb_get_option": (_int, [_int]),
     "qpb_fp64_fma_probe": (_int, [ctypes.c_int64, _vp, ctypes.POINTER(_dbl), _vp]),
     "qpb_state_plan_create": (_int, [ctypes.POINTER(_vp), _int, _int, _vp, _vp, _vp]),
     "qpb_state_plan_destroy": (_int, [_vp]),
@@ -60,8 +62,39 @@ SIGNATURES = {
 }
 
 
+# QPB_OPT_* of include/quantpy_b200.h (kernel-selection toggles for tests and profiling)
+OPTIONS = {"NO_TAIL_MERGE": 0, "NO_HS_FUSION": 1, "NO_PAULI_KERNEL": 2, "NO_CONST_KERNEL": 3, "NO_AXIS_KERNEL": 4,
+           "NO_DMMA_GEMM": 5, "NO_ROW_JACOBI": 6, "NO_PACKED_JACOBI": 7, "NO_LIN_SMALL": 8, "SAMPLER": 9,
+           "MLE_BLOCKS_PER_SM": 10, "MLE_LANES": 11, "NO_TILED_MLE": 12, "MLE_PARK_AGE": 13, "MLE_PARK_LIVE": 14,
+           "MLE_W_WARPS": 15, "MLE_PARK_PLATEAU": 16}
+SAMPLERS = {"auto": 0, "alias": 1, "binomial": 2}
+
+
 class NativeError(RuntimeError):
     pass
+
+
+def set_option(name, value):
+    """Set a kernel-selection toggle (tests / profiling); returns the previous value."""
+    lib = load_library()
+    old = lib.qpb_get_option(OPTIONS[name])
+    check(lib.qpb_set_option(OPTIONS[name], int(value)))
+    return old
+
+
+class option:
+    """Context manager: `with option("NO_TAIL_MERGE", 1): ...` restores the previous value on exit."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.old = set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.old)
+        return False
 
 
 def load_library():

@@ -4,7 +4,10 @@
 #include <cstdio>
 #include <map>
 #include <mutex>
+#include <cstdlib>
+#include <cstring>
 #include <utility>
+#include <vector>
 
 #include "../../include/quantpy_b200.h"
 #include "common.cuh"
@@ -27,38 +30,82 @@ int check_cuda(cudaError_t e, const char* what) {
     return QPB_ERR_CUDA;
 }
 
-void* scratch(cudaStream_t st, int slot, size_t bytes) {
+// Grow-only scratch, one buffer per (device, stream, slot).  A buffer that has to grow is not freed (a kernel
+// launched earlier on the stream, or a host thread that was handed the pointer a moment ago, may still use it):
+// it is retired to a per-device list that lives as long as the process.  Growth is geometric, so the retired
+// bytes are bounded by the largest request.
+void* scratch(cudaStream_t st, int slot, size_t bytes, bool* fresh) {
     struct Buf {
         void* p = nullptr;
         size_t n = 0;
     };
-    static std::mutex mu;
-    static std::map<std::pair<cudaStream_t, int>, Buf> pool;
-    std::lock_guard<std::mutex> lock(mu);
-    Buf& b = pool[std::make_pair(st, slot)];
-    if (b.n < bytes) {
-        if (b.p) {
-            cudaStreamSynchronize(st);  // earlier kernels on this stream may still read the old buffer
-            cudaFree(b.p);
-            b.p = nullptr;
-            b.n = 0;
+    struct Key {
+        int dev;
+        cudaStream_t st;
+        int slot;
+        bool operator<(const Key& o) const {
+            if (dev != o.dev) return dev < o.dev;
+            if (st != o.st) return st < o.st;
+            return slot < o.slot;
         }
+    };
+    static std::mutex mu;
+    static std::map<Key, Buf> pool;
+    static std::vector<void*> retired;
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "scratch cudaGetDevice") != QPB_OK) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    Buf& b = pool[Key{dev, st, slot}];
+    if (fresh) *fresh = false;
+    if (b.n < bytes) {
+        if (fresh) *fresh = true;
         size_t want = bytes < 4096 ? 4096 : bytes;
-        if (check_cuda(cudaMalloc(&b.p, want), "scratch cudaMalloc") != QPB_OK) return nullptr;
+        if (want < 2 * b.n) want = 2 * b.n;
+        void* p = nullptr;
+        if (check_cuda(cudaMalloc(&p, want), "scratch cudaMalloc") != QPB_OK) return nullptr;
+        if (b.p) retired.push_back(b.p);
+        b.p = p;
         b.n = want;
     }
     return b.p;
 }
 
 int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
+    static std::mutex mu;
+    static std::map<int, int> per_device;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = per_device.find(dev);
+    if (it != per_device.end()) return it->second;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    per_device[dev] = sms;
     return sms;
 }
+
+// Kernel-selection toggles (tests and profiling only).  Read from the environment ONCE, when the library is
+// loaded; qpb_set_option changes them afterwards.  Nothing on the launch path calls getenv.
+static std::atomic<int> g_options[QPB_OPT_COUNT_];
+static const char* const kOptionEnv[QPB_OPT_COUNT_] = {
+    "QPB_NO_TAIL_MERGE", "QPB_NO_HS_FUSION", "QPB_NO_PAULI_KERNEL", "QPB_NO_CONST_KERNEL", "QPB_NO_AXIS_KERNEL",
+    "QPB_NO_DMMA_GEMM",  "QPB_NO_ROW_JACOBI", "QPB_NO_PACKED_JACOBI", "QPB_NO_LIN_SMALL",  "QPB_SAMPLER",
+    "QPB_MLE_BLOCKS_PER_SM", "QPB_MLE_LANES", "QPB_NO_TILED_MLE",
+    "QPB_MLE_PARK_AGE", "QPB_MLE_PARK_LIVE", "QPB_MLE_W_WARPS", "QPB_MLE_PARK_PLATEAU"};
+static const bool g_options_loaded = [] {
+    for (int i = 0; i < QPB_OPT_COUNT_; ++i) {
+        const char* e = getenv(kOptionEnv[i]);
+        int v = 0;
+        if (e && *e) {
+            if (i == QPB_OPT_SAMPLER) v = !strcmp(e, "alias") ? 1 : (!strcmp(e, "binomial") ? 2 : 0);
+            else if (i >= QPB_OPT_MLE_BLOCKS_PER_SM && i != QPB_OPT_NO_TILED_MLE) v = atoi(e);
+            else v = 1;
+        }
+        g_options[i].store(v);
+    }
+    return true;
+}();
+int option(int which) { return (which >= 0 && which < QPB_OPT_COUNT_) ? g_options[which].load(std::memory_order_relaxed) : 0; }
 
 }  // namespace qpb
 
@@ -90,6 +137,12 @@ int qpb_fp64_fma_probe(int64_t iters_per_thread, double* sink, double* flops_out
 }
 
 int qpb_abi_version(void) { return QPB_ABI_VERSION; }
+int qpb_set_option(int which, int value) {
+    QPB_REQUIRE(which >= 0 && which < QPB_OPT_COUNT_, "unknown option %d", which);
+    qpb::g_options[which].store(value);
+    return QPB_OK;
+}
+int qpb_get_option(int which) { return qpb::option(which); }
 const char* qpb_last_error(void) { return qpb::g_err; }
 int64_t qpb_launch_count(void) { return qpb::g_launches.load(); }
 void qpb_reset_launch_count(void) { qpb::g_launches.store(0); }

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/quantpy_b200.h"
+
 #include <atomic>
 #include <cstdio>
 
@@ -17,12 +19,14 @@ namespace qpb {
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int num_sms();
+int option(int which);  // QPB_OPT_* toggle (include/quantpy_b200.h); cached, no getenv on the launch path
 extern std::atomic<int64_t> g_launches;
 
-// Grow-only device scratch, one buffer per (stream, slot): kernels of one call reuse it in stream order, so no
-// allocation (and no allocator-induced gap after an idle period) happens on the hot path.  Returns nullptr
-// and sets the error on failure.
-void* scratch(cudaStream_t st, int slot, size_t bytes);
+// Grow-only device scratch, one buffer per (device, stream, slot): kernels of one call reuse it in stream order,
+// so no allocation (and no allocator-induced gap after an idle period) happens on the hot path.  Returns nullptr
+// and sets the error on failure.  *fresh (optional) is set when the returned buffer was allocated by this call,
+// i.e. its contents are undefined.
+void* scratch(cudaStream_t st, int slot, size_t bytes, bool* fresh = nullptr);
 
 // Call right after a <<<>>> launch: counts it and surfaces launch-configuration errors.
 #define QPB_LAUNCHED(name)                                     \

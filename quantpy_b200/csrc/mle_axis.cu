@@ -567,7 +567,7 @@ int axis_plan_setup(qpb_state_plan* plan, const double* A_host) {
 
 int launch_mle_axis(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                     double tol, double* rho, int32_t* iters, cudaStream_t st) {
-    if (!plan->axis_ok || getenv("QPB_NO_AXIS_KERNEL")) return QPB_ERR_UNSUPPORTED;
+    if (!plan->axis_ok || option(QPB_OPT_NO_AXIS_KERNEL)) return QPB_ERR_UNSUPPORTED;
     if (plan->n == 3) return launch_axis<3>(plan, B, counts, rho0, max_iter, tol, rho, iters, st);
     if (plan->n == 4) return launch_axis<4>(plan, B, counts, rho0, max_iter, tol, rho, iters, st);
     return QPB_ERR_UNSUPPORTED;

@@ -24,9 +24,8 @@ constexpr int kSmallThreads = 128;
 // flow through each lane (better balance) and that the straggler tail runs with less pipe sharing.
 constexpr int kMaxBlocksPerSmDefault = 2;
 static int max_blocks_per_sm() {
-    const char* e = getenv("QPB_MLE_BLOCKS_PER_SM");
-    const int v = e ? atoi(e) : kMaxBlocksPerSmDefault;
-    return v < 1 ? 1 : v;
+    const int v = option(QPB_OPT_MLE_BLOCKS_PER_SM);
+    return v < 1 ? kMaxBlocksPerSmDefault : v;
 }
 #define kMaxBlocksPerSm max_blocks_per_sm()
 
@@ -389,403 +388,17 @@ static int launch_const(const qpb_state_plan* plan, int B, const int32_t* counts
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// Pauli-axis POVMs on two qubits ('proj', 'proj-set', 'proj4', any shot weights): every effect is
-//     E_k = c_k (1 + s1 sigma_a1) (x) (1 + s2 sigma_a2),   a in {X,Y,Z}, s = +-1,
-// so with S_ij = Tr(sigma_i (x) sigma_j rho) the probabilities are p_k = c_k (S_00 + s1 S_a0 + s2 S_0b + s1 s2 S_ab)
-// and R = sum_k w_k (1 + s1 sigma_a1) (x) (1 + s2 sigma_a2) has Pauli coefficients that are signed sums of
-// the weights.  The whole K x D contraction collapses to ~200 additions and there is NO table: the only
-// per-iteration loads are the sample's 36 frequencies from shared memory.  Effects are addressed by the
-// canonical slot (alpha, beta), alpha = 2*(axis-1) + (sign<0); the plan maps count columns to slots.
-// ------------------------------------------------------------------------------------------------
-namespace pauli2 {
-__host__ __device__ constexpr int phase(int i, int a, int b) {  // sigma_i[a][b] = i^phase, or -1 if zero
-    int k = 0;
-    for (int j = 0; j < 2; ++j) {
-        const int sh = 1 - j;
-        const int dig = (i >> (2 * sh)) & 3, aj = (a >> sh) & 1, bj = (b >> sh) & 1;
-        if (dig == 0) {
-            if (aj != bj) return -1;
-        } else if (dig == 1) {
-            if (aj == bj) return -1;
-        } else if (dig == 2) {
-            if (aj == bj) return -1;
-            k += (aj == 0) ? 3 : 1;
-        } else {
-            if (aj != bj) return -1;
-            k += 2 * aj;
-        }
-    }
-    return k & 3;
-}
-__host__ __device__ constexpr int re_of(int ph) { return ph == 0 ? 1 : (ph == 2 ? -1 : 0); }
-__host__ __device__ constexpr int im_of(int ph) { return ph == 1 ? 1 : (ph == 3 ? -1 : 0); }
-// coefficient of packed h[e] in S_i = Tr(sigma_i rho)
-__host__ __device__ constexpr int s_coef(int i, int e) {
-    const int a = e / 4, b = e % 4;
-    if (a == b) return re_of(phase(i, a, a));
-    if (a < b) return 2 * re_of(phase(i, b, a));
-    return -2 * im_of(phase(i, a, b));
-}
-// coefficient of g_i in packed(sum_i g_i sigma_i)[e]
-__host__ __device__ constexpr int r_coef(int e, int i) {
-    const int a = e / 4, b = e % 4;
-    if (a <= b) return re_of(phase(i, a, b));
-    return im_of(phase(i, b, a));
-}
-template <int I, int E>
-struct SC {
-    static constexpr int v = s_coef(I, E);
-};
-template <int E, int I>
-struct RC {
-    static constexpr int v = r_coef(E, I);
-};
-template <int I, int E = 0>
-__device__ __forceinline__ double s_sum(const double (&h)[16], double acc) {
-    if constexpr (E == 16) {
-        return acc;
-    } else {
-        if constexpr (SC<I, E>::v != 0) acc = fma((double)SC<I, E>::v, h[E], acc);
-        return s_sum<I, E + 1>(h, acc);
-    }
-}
-template <int E, int I = 0>
-__device__ __forceinline__ double r_sum(const double (&g)[16], double acc) {
-    if constexpr (I == 16) {
-        return acc;
-    } else {
-        if constexpr (RC<E, I>::v != 0) acc = fma((double)RC<E, I>::v, g[I], acc);
-        return r_sum<E, I + 1>(g, acc);
-    }
-}
-template <int I = 0>
-__device__ __forceinline__ void all_s(const double (&h)[16], double (&s)[16]) {
-    if constexpr (I < 16) {
-        s[I] = s_sum<I>(h, 0.0);
-        all_s<I + 1>(h, s);
-    }
-}
-template <int E = 0>
-__device__ __forceinline__ void all_r(const double (&g)[16], double (&R)[16]) {
-    if constexpr (E < 16) {
-        R[E] = r_sum<E>(g, 0.0);
-        all_r<E + 1>(g, R);
-    }
-}
-}  // namespace pauli2
-
-struct PauliParams {
-    double epsp[36];      // 1e-10 / c_k per slot (1.0 for unused slots)
-    int slot_of_col[36];  // canonical slot of count column k
-    int K;
-    int uniform;          // all used slots have the same guard (then every entry of epsp holds it)
-};
-
-// Tail merging.  The kernel runs ONE 256-thread CTA per SM: warps w and w+4 sit on the same scheduler.  While the
-// queue has work both are full; once it is empty each holds a few long-running samples and the two instruction
-// streams halve each other's FP64 issue rate.  The upper warp ("donor") therefore hands its remaining samples to
-// idle lanes of the lower warp ("receiver") through a shared-memory mailbox as soon as it has at most kDonateMax
-// of them, and exits.  A sample's iteration sequence is untouched, so results are bit-identical.
-// state word per pair: 0 open | 3 donor writing | 1 mail ready | 4 mail taken | 2 receiver gone
-constexpr int kPauliThreads = 256;
-constexpr int kDonateMax = 16;
-struct TailMail {
-    double h[kDonateMax][16];
-    long b[kDonateMax];
-    int it[kDonateMax];
-    int col[kDonateMax];
-};
-
-template <bool UNIFORM_GUARD>  // all used slots share one 1e-10/c: fold it into S_00 instead of 36 additions
-__global__ void __launch_bounds__(kPauliThreads, 1)
-k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, int B, const int32_t* __restrict__ counts,
-                 const double* __restrict__ rho0, int max_iter, double tol, double* __restrict__ rho,
-                 int32_t* __restrict__ iters, unsigned int* __restrict__ queue, int merge_tail,
-                 const double* __restrict__ hs_ref, double* __restrict__ hs_dist) {
-    constexpr int d = 4, D = 16;
-    extern __shared__ __align__(16) double sm[];
-    double* fs = sm;  // [36][kPauliThreads], column = owning thread at load time
-    __shared__ TailMail mail[4];
-    __shared__ int pair_state[4];
-    __shared__ int mail_count[4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pair = warp & 3;
-    const bool donor = warp >= 4;
-    const int K = pp.K;
-    for (int sl = 0; sl < 36; ++sl) fs[sl * kPauliThreads + tid] = 0.0;
-    if (tid < 4) pair_state[tid] = 0;
-    __syncthreads();
-
-    double h[D];
-    int it = 0;
-    int col = tid;      // fs column of the sample this lane owns
-    long b = -1;
-    bool alive = true;  // false once the queue ran dry for this lane
-    bool can_merge = merge_tail != 0 && blockDim.x == kPauliThreads;
-    bool drained = false;  // warp-uniform: some lane has seen the queue empty (it never refills again)
-    const double tol2 = tol * tol;
-
-    while (true) {
-        // ---- refill lanes without work -------------------------------------------------------
-        const bool want = alive && b < 0;
-        const unsigned need = __ballot_sync(0xffffffffu, want);
-        if (need) {
-            unsigned base = 0;
-            const int leader = __ffs(need) - 1;
-            if (lane == leader) base = atomicAdd(queue, (unsigned)__popc(need));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (want) {
-                const long nb = (long)base + __popc(need & ((1u << lane) - 1u));
-                if (nb < B) {
-                    b = nb;
-                    it = 0;
-                    col = tid;
-                    // all K count loads are issued together (independent, predicated), then normalised
-                    const int32_t* c = counts + b * K;
-                    int cc[36];
-#pragma unroll
-                    for (int k = 0; k < 36; ++k) cc[k] = (k < K) ? c[k] : 0;
-                    int tot = 0;
-#pragma unroll
-                    for (int k = 0; k < 36; ++k) tot += cc[k];
-                    const FreqDiv freq((double)tot);
-#pragma unroll
-                    for (int k = 0; k < 36; ++k)
-                        if (k < K) fs[pp.slot_of_col[k] * kPauliThreads + tid] = freq((double)cc[k]);
-                    if (rho0) {
-                        const double2* r0 = reinterpret_cast<const double2*>(rho0) + b * D;
-#pragma unroll
-                        for (int a = 0; a < d; ++a)
-#pragma unroll
-                            for (int bb = a; bb < d; ++bb) {
-                                const double2 z = r0[a * d + bb];
-                                h[a * d + bb] = z.x;
-                                if (a != bb) h[bb * d + a] = z.y;
-                            }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < D; ++e) h[e] = (e / d == e % d) ? 1.0 / d : 0.0;
-                    }
-                } else {
-                    alive = false;
-                }
-            }
-        }
-        unsigned active = __ballot_sync(0xffffffffu, b >= 0);
-        if (!drained) drained = __any_sync(0xffffffffu, !alive);
-
-        // ---- tail merging (only once the queue is empty) ----------------------------------------
-        if (can_merge && drained) {
-            if (donor) {
-                const int nact = __popc(active);
-                if (nact > 0 && nact <= kDonateMax) {
-                    int old = 0;
-                    if (lane == 0) old = atomicCAS(&pair_state[pair], 0, 3);
-                    old = __shfl_sync(0xffffffffu, old, 0);
-                    if (old == 0) {
-                        if (b >= 0) {
-                            const int slot = __popc(active & ((1u << lane) - 1u));
-#pragma unroll
-                            for (int e = 0; e < D; ++e) mail[pair].h[slot][e] = h[e];
-                            mail[pair].b[slot] = b;
-                            mail[pair].it[slot] = it;
-                            mail[pair].col[slot] = col;
-                        }
-                        __syncwarp();
-                        if (lane == 0) {
-                            mail_count[pair] = nact;
-                            __threadfence_block();
-                            atomicExch(&pair_state[pair], 1);
-                        }
-                        b = -1;
-                        active = 0;
-                    } else {
-                        can_merge = false;  // the receiver has already left: finish alone
-                    }
-                }
-            } else {
-                int st = 0;
-                if (lane == 0) {
-                    st = *(volatile int*)&pair_state[pair];
-                    if (active == 0 && st != 1) {
-                        // about to leave: close the pair, or wait for a donor that is writing its mail
-                        const int old = atomicCAS(&pair_state[pair], 0, 2);
-                        st = old;
-                        while (st == 3) st = *(volatile int*)&pair_state[pair];
-                    }
-                }
-                st = __shfl_sync(0xffffffffu, st, 0);
-                if (st == 1) {
-                    __threadfence_block();
-                    const int cnt = mail_count[pair];
-                    const unsigned idle = ~active;
-                    if (__popc(idle) >= cnt) {
-                        const int rank = __popc(idle & ((1u << lane) - 1u));
-                        if (b < 0 && rank < cnt) {
-#pragma unroll
-                            for (int e = 0; e < D; ++e) h[e] = mail[pair].h[rank][e];
-                            b = mail[pair].b[rank];
-                            it = mail[pair].it[rank];
-                            col = mail[pair].col[rank];
-                        }
-                        __syncwarp();
-                        if (lane == 0) atomicExch(&pair_state[pair], 4);
-                        active = __ballot_sync(0xffffffffu, b >= 0);
-                    }
-                } else if (st != 0 && st != 3) {
-                    can_merge = false;  // pair closed (mail taken, or we closed it ourselves)
-                }
-            }
-        }
-        if (active == 0) break;
-
-        // ---- one R.rho.R iteration (lanes without a sample are predicated off) ---------------
-        bool finished = false;
-        if (b >= 0) {
-            if (max_iter <= 0) {
-                finished = true;
-            } else {
-                double S[16], g[16];
-                pauli2::all_s(h, S);
-                if (UNIFORM_GUARD) S[0] += pp.epsp[0];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) g[e] = 0.0;
-#pragma unroll
-                for (int al = 0; al < 6; ++al) {
-                    const int a = al / 2 + 1;
-                    const bool neg_a = al & 1;
-                    double t[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) t[j] = neg_a ? S[j] - S[a * 4 + j] : S[j] + S[a * 4 + j];
-                    double w[6];
-#pragma unroll
-                    for (int be = 0; be < 6; ++be) {
-                        const int bq = be / 2 + 1;
-                        const double q = (be & 1) ? t[0] - t[bq] : t[0] + t[bq];
-                        w[be] = UNIFORM_GUARD ? q : q + pp.epsp[al * 6 + be];
-                    }
-#pragma unroll
-                    for (int be = 0; be < 6; ++be) w[be] = fs[(al * 6 + be) * kPauliThreads + col] * fast_rcp(w[be]);
-                    double u[4];
-                    u[0] = ((w[0] + w[1]) + (w[2] + w[3])) + (w[4] + w[5]);
-                    u[1] = w[0] - w[1];
-                    u[2] = w[2] - w[3];
-                    u[3] = w[4] - w[5];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        g[j] += u[j];
-                        if (neg_a) g[a * 4 + j] -= u[j];
-                        else g[a * 4 + j] += u[j];
-                    }
-                }
-                double R[D];
-                pauli2::all_r(g, R);
-                double hn[D];
-                rrr_apply<d>(R, h, hn);
-                const double tr = (hn[0] + hn[5]) + (hn[10] + hn[15]);
-                const double inv = fast_rcp(tr);
-                double dl[4] = {0.0, 0.0, 0.0, 0.0};  // four partial sums: no 16-deep dependent FMA chain
-#pragma unroll
-                for (int e = 0; e < D; ++e) {
-                    const double v = hn[e] * inv;
-                    const double df = v - h[e];
-                    dl[e & 3] = fma((e / d == e % d) ? df : 2.0 * df, df, dl[e & 3]);
-                    h[e] = v;
-                }
-                const double del = (dl[0] + dl[1]) + (dl[2] + dl[3]);
-                ++it;
-                finished = (del < tol2) || (it >= max_iter);
-            }
-        }
-        if (finished) {
-            if (rho) {
-                double2* out = reinterpret_cast<double2*>(rho) + b * D;
-#pragma unroll
-                for (int a = 0; a < d; ++a)
-#pragma unroll
-                    for (int bb = 0; bb < d; ++bb) {
-                        double2 z;
-                        z.x = Packed<d>::re(h, a, bb);
-                        z.y = Packed<d>::im(h, a, bb);
-                        out[a * d + bb] = z;
-                    }
-            }
-            if (hs_dist) {
-                // hs_dst(rho, ref) = sqrt(|Tr (rho - ref)^2|) / sqrt 2, no conjugate (quantpy/geometry.py:5-17); same
-                // formula as k_distance, evaluated here so that the bootstrap needs neither the state nor a fourth kernel
-                double sr = 0.0, si = 0.0;
-#pragma unroll
-                for (int a = 0; a < d; ++a)
-#pragma unroll
-                    for (int bb = 0; bb < d; ++bb) {
-                        const double ur = Packed<d>::re(h, a, bb) - __ldg(hs_ref + 2 * (a * d + bb));
-                        const double ui = Packed<d>::im(h, a, bb) - __ldg(hs_ref + 2 * (a * d + bb) + 1);
-                        const double vr = Packed<d>::re(h, bb, a) - __ldg(hs_ref + 2 * (bb * d + a));
-                        const double vi = Packed<d>::im(h, bb, a) - __ldg(hs_ref + 2 * (bb * d + a) + 1);
-                        sr += ur * vr - ui * vi;
-                        si += ur * vi + ui * vr;
-                    }
-                hs_dist[b] = sqrt(sqrt(sr * sr + si * si)) / sqrt(2.0);
-            }
-            if (iters) iters[b] = it;
-            b = -1;
-        }
-    }
-}
-
-// Recognise a two-qubit Pauli-axis POVM from the Bloch-basis table A [K][16] (host copy).
-static bool detect_pauli2(const double* A, int K, PauliParams* pp) {
-    if (K < 1 || K > 36) return false;
-    bool used[36] = {false};
-    for (int sl = 0; sl < 36; ++sl) pp->epsp[sl] = 1.0;
-    pp->K = K;
-    for (int k = 0; k < K; ++k) {
-        const double* r = A + (size_t)k * 16;
-        const double c = r[0];
-        if (!(c > 0.0)) return false;
-        int a1 = 0, a2 = 0, s1 = 0, s2 = 0;
-        for (int i = 1; i < 4; ++i) {
-            if (r[i * 4] != 0.0) {
-                if (a1 || fabs(fabs(r[i * 4]) - c) > 1e-14 * c) return false;
-                a1 = i;
-                s1 = r[i * 4] > 0 ? 1 : -1;
-            }
-            if (r[i] != 0.0) {
-                if (a2 || fabs(fabs(r[i]) - c) > 1e-14 * c) return false;
-                a2 = i;
-                s2 = r[i] > 0 ? 1 : -1;
-            }
-        }
-        if (!a1 || !a2) return false;
-        for (int i = 1; i < 4; ++i)
-            for (int j = 1; j < 4; ++j) {
-                const double want = (i == a1 && j == a2) ? s1 * s2 * c : 0.0;
-                if (fabs(r[i * 4 + j] - want) > 1e-14 * c) return false;
-            }
-        const int slot = (2 * (a1 - 1) + (s1 < 0)) * 6 + (2 * (a2 - 1) + (s2 < 0));
-        if (used[slot]) return false;
-        used[slot] = true;
-        pp->slot_of_col[k] = slot;
-        pp->epsp[slot] = kLogGuard / c;
-    }
-    const double first = pp->epsp[pp->slot_of_col[0]];
-    pp->uniform = 1;
-    for (int k = 0; k < K; ++k)
-        if (pp->epsp[pp->slot_of_col[k]] != first) pp->uniform = 0;
-    if (pp->uniform)
-        for (int sl = 0; sl < 36; ++sl) pp->epsp[sl] = first;  // unused slots have f = 0, any positive guard works
-    return true;
-}
+// Two-qubit Pauli-axis POVMs have their own table-free kernel (mle_pauli2.cu).
+bool plan_is_pauli2(const qpb_state_plan* plan);
+int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
+                      double tol, double* rho, int32_t* iters, cudaStream_t st, const double* hs_ref, double* hs_dist,
+                      bool* hs_done, int hs_store_rho);
 
 // Which kernel qpb_mle_rrr will run for this plan (also exported through qpb_mle_variant for bench.py).
 int mle_variant(const qpb_state_plan* plan) {
-    if (plan->n > 2) return (plan->axis_ok && !getenv("QPB_NO_AXIS_KERNEL")) ? QPB_MLE_AXIS : QPB_MLE_GENERIC;
-    if (plan->n == 2 && plan->A_host && !getenv("QPB_NO_PAULI_KERNEL")) {
-        PauliParams pp;
-        if (detect_pauli2(plan->A_host, plan->K, &pp)) return QPB_MLE_PAULI2;
-    }
-    if (plan->Ar_host && !getenv("QPB_NO_CONST_KERNEL")) {
+    if (plan->n > 2) return (plan->axis_ok && !option(QPB_OPT_NO_AXIS_KERNEL)) ? QPB_MLE_AXIS : QPB_MLE_GENERIC;
+    if (plan->n == 2 && plan->A_host && !option(QPB_OPT_NO_PAULI_KERNEL) && plan_is_pauli2(plan)) return QPB_MLE_PAULI2;
+    if (plan->Ar_host && !option(QPB_OPT_NO_CONST_KERNEL)) {
         if ((plan->n == 2 && (plan->K == 36 || plan->K == 16)) || (plan->n == 1 && (plan->K == 6 || plan->K == 4)))
             return QPB_MLE_CONST;
     }
@@ -800,30 +413,15 @@ int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, c
     if (plan->n > 2) return QPB_ERR_UNSUPPORTED;
     const size_t smem = sizeof(double) * ((size_t)plan->K * plan->D + (size_t)plan->K * kSmallThreads);
     if (smem > 200 * 1024) return QPB_ERR_UNSUPPORTED;
-    unsigned int* queue = static_cast<unsigned int*>(scratch(st, 0, sizeof(unsigned int)));
+    if (plan->n == 2 && plan->A_host && !option(QPB_OPT_NO_PAULI_KERNEL)) {
+        const int rc = launch_mle_pauli2(plan, B, counts, rho0, max_iter, tol, rho, iters, st, hs_ref, hs_dist, hs_done,
+                                         hs_store_rho);
+        if (rc != QPB_ERR_UNSUPPORTED) return rc;
+    }
+    unsigned int* queue = static_cast<unsigned int*>(scratch(st, 6, sizeof(unsigned int)));
     if (!queue) return QPB_ERR_NOMEM;
     QPB_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), st));
-    if (plan->n == 2 && plan->A_host && !getenv("QPB_NO_PAULI_KERNEL")) {
-        PauliParams pp;
-        if (detect_pauli2(plan->A_host, plan->K, &pp)) {
-            const size_t smem = sizeof(double) * 36 * kPauliThreads;
-            auto pk = pp.uniform ? k_mle_rrr_pauli2<true> : k_mle_rrr_pauli2<false>;
-            QPB_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            long blocks = num_sms();  // one 8-warp CTA per SM: warps w and w+4 share a scheduler (tail merging)
-            const long need = ((long)B + kPauliThreads - 1) / kPauliThreads;
-            if (blocks > need) blocks = need;
-            const int merge = getenv("QPB_NO_TAIL_MERGE") ? 0 : 1;
-            const bool fuse = hs_ref && hs_dist && hs_done && !getenv("QPB_NO_HS_FUSION");
-            // with the distance fused and no caller for the states, they are not written at all
-            double* rho_dst = (fuse && hs_store_rho == 0) ? nullptr : rho;
-            pk<<<(int)blocks, kPauliThreads, smem, st>>>(pp, B, counts, rho0, max_iter, tol, rho_dst, iters, queue, merge,
-                                                        fuse ? hs_ref : nullptr, fuse ? hs_dist : nullptr);
-            QPB_LAUNCHED("k_mle_rrr_pauli2");
-            if (fuse) *hs_done = true;
-            return QPB_OK;
-        }
-    }
-    if (plan->Ar_host && !getenv("QPB_NO_CONST_KERNEL")) {
+    if (plan->Ar_host && !option(QPB_OPT_NO_CONST_KERNEL)) {
         int rc = QPB_ERR_UNSUPPORTED;
         if (plan->n == 2 && plan->K == 36) rc = launch_const<2, 36>(plan, B, counts, rho0, max_iter, tol, rho, iters, queue, st);
         else if (plan->n == 2 && plan->K == 16) rc = launch_const<2, 16>(plan, B, counts, rho0, max_iter, tol, rho, iters, queue, st);

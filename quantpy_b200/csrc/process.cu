@@ -291,7 +291,7 @@ int qpb_lifp_cptp(const qpb_process_plan* plan, int B, const int32_t* counts, in
     QPB_REQUIRE(counts && choi, "NULL buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const int cols = plan->S * plan->K;
-    if (!getenv("QPB_NO_DMMA_GEMM")) {
+    if (!option(QPB_OPT_NO_DMMA_GEMM)) {
         // choi [B][2 d^4] = freq [B][S*K] * LinvT [S*K][2 d^4], frequencies normalised per input state
         int rc = launch_gemm_counts(B, 2 * plan->d4, cols, plan->K, counts, plan->LinvT, choi, st);
         if (rc != QPB_OK) return rc;

@@ -346,12 +346,12 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
     // O(O) conditional binomials beat O(shots) alias draws unless there are very few shots per outcome
     long max_shots = 0;
     for (int m = 0; m < P; ++m) max_shots = shots.n[m] > max_shots ? shots.n[m] : max_shots;
-    const char* force = getenv("QPB_SAMPLER");
+    const int force = option(QPB_OPT_SAMPLER);
     // measured on B200 (tools/bench_configs.py): the binomial chain is sequential in O (0.0084 ms per outcome at
     // 1e5 threads) while the alias kernel scales with the shots (1.2 ms per 1e4 shots x 1e5 warps)
     bool use_binomial = max_shots > 64L * O;
-    if (force && force[0] == 'a') use_binomial = false;
-    if (force && force[0] == 'b') use_binomial = true;
+    if (force == 1) use_binomial = false;
+    if (force == 2) use_binomial = true;
     if (use_binomial) {
         const long items = (long)B * P;
         const int threads = 128;

@@ -504,7 +504,7 @@ int launch_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts,
     if (rc != QPB_OK) return rc;
     const int grid = grid_for_warps(B, warps, 4);
     const double* h_in = nullptr;
-    if (plan->n >= 3 && !getenv("QPB_NO_DMMA_GEMM")) {
+    if (plan->n >= 3 && !option(QPB_OPT_NO_DMMA_GEMM)) {
         // batched inversion on the FP64 tensor cores: H [B][D] = freq [B][K] * LhT [K][D]
         double* H = static_cast<double*>(scratch(st, 3, sizeof(double) * (size_t)B * plan->D));
         if (!H) return QPB_ERR_NOMEM;
@@ -514,9 +514,9 @@ int launch_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts,
     }
     // d = 8, 16: one lane per matrix row, state in registers (measured per 1e5 / 1e4 matrices: 1.35 -> 0.95 ms against
     // the shared-memory kernel at d = 8, 2.1 -> 1.4 ms against the warp-per-matrix kernel at d = 16)
-    if (h_in && physical && (plan->d == 8 || plan->d == 16) && !getenv("QPB_NO_ROW_JACOBI"))
+    if (h_in && physical && (plan->d == 8 || plan->d == 16) && !option(QPB_OPT_NO_ROW_JACOBI))
         return launch_project_rows(plan->d, B, h_in, rho, st);
-    if (h_in && plan->d == 8 && !getenv("QPB_NO_PACKED_JACOBI")) {
+    if (h_in && plan->d == 8 && !option(QPB_OPT_NO_PACKED_JACOBI)) {
         // 4 samples per warp, G = d = 8 lanes each (measured: 2.0 -> 1.35 ms per 1e5 matrices; at d = 16 two
         // matrices per warp were slower than one, 2.2 vs 1.9 ms per 1e4, so n = 4 keeps the warp-per-matrix kernel)
         const int d = plan->d;
@@ -650,7 +650,7 @@ int qpb_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts, in
     QPB_REQUIRE(B >= 0, "negative batch");
     if (B == 0) return QPB_OK;
     QPB_REQUIRE(counts && rho, "NULL buffer");
-    int rc = getenv("QPB_NO_LIN_SMALL") ? QPB_ERR_UNSUPPORTED
+    int rc = option(QPB_OPT_NO_LIN_SMALL) ? QPB_ERR_UNSUPPORTED
                                         : launch_lin_project_small(plan, B, counts, physical, rho, (cudaStream_t)stream);
     if (rc == QPB_ERR_UNSUPPORTED) rc = launch_lin_project(plan, B, counts, physical, rho, (cudaStream_t)stream);
     return rc;

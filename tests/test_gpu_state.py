@@ -56,15 +56,25 @@ def test_probabilities_match_reference(qp, golden, case):
 
 
 @pytest.fixture(params=["binomial", "alias"])
-def sampler_kind(request, monkeypatch):
-    """Both multinomial kernels are held to the same distributional tests (QPB_SAMPLER forces one)."""
-    monkeypatch.setenv("QPB_SAMPLER", request.param)
-    return request.param
+def sampler_kind(request):
+    """Both multinomial kernels are held to the same distributional tests (the SAMPLER option forces one)."""
+    from quantpy_b200 import _native as nt
+
+    with nt.option("SAMPLER", nt.SAMPLERS[request.param]):
+        yield request.param
+
+
+@pytest.fixture
+def forced_binomial():
+    from quantpy_b200 import _native as nt
+
+    with nt.option("SAMPLER", nt.SAMPLERS["binomial"]):
+        yield
 
 
 @pytest.mark.parametrize("n_shots,p", [(10000, 0.3), (10000, 1 / 36), (10000, 0.001), (10000, 0.9995), (100, 0.5),
                                        (57, 0.93), (1000000, 0.41), (3, 0.2), (2000, 0.015), (500, 0.06)])
-def test_binomial_kernel_matches_exact_pmf(qp, monkeypatch, n_shots, p):
+def test_binomial_kernel_matches_exact_pmf(qp, forced_binomial, n_shots, p):
     """O = 2 makes the multinomial a single binomial draw: chi-square against scipy.stats.binom over
     both regimes (inversion for n*min(p,1-p) < 30, BTPE otherwise) and the p > 1/2 reflection."""
     import torch
@@ -72,7 +82,6 @@ def test_binomial_kernel_matches_exact_pmf(qp, monkeypatch, n_shots, p):
 
     from quantpy_b200 import engine
 
-    monkeypatch.setenv("QPB_SAMPLER", "binomial")
     B = 400000
     probs = torch.tensor([p, 1 - p], dtype=torch.float64, device="cuda")
     counts = engine.sample_counts(probs, B, 1, 2, [n_shots], seed=7 + n_shots, offset=0).cpu().numpy()[:, 0, :]
@@ -271,13 +280,23 @@ def test_mle_tolerance_mode_matches_oracle(qp, n, povm, B, tol, max_iter):
     (1, "proj-set", [], 2), (1, "proj-set", ["CONST"], 1),
     (3, "proj", [], 4), (3, "proj", ["AXIS"], 0), (3, "proj-set", [], 4), (3, "sic", [], 0), (4, "proj", [], 4),
 ])
-def test_every_mle_kernel_variant_matches_oracle(qp, monkeypatch, n, povm, disable, expect):
+def test_every_mle_kernel_variant_matches_oracle(qp, n, povm, disable, expect):
     """qpb_mle_rrr dispatches on the POVM's structure; every variant is the same update to 1e-10."""
+    import contextlib
+
     from quantpy_b200 import _native as nt
     from quantpy_b200 import engine
 
-    for name in disable:
-        monkeypatch.setenv(f"QPB_NO_{name}_KERNEL", "1")
+    with contextlib.ExitStack() as stack:
+        for name in disable:
+            stack.enter_context(nt.option(f"NO_{name}_KERNEL", 1))
+        _check_mle_variant(qp, n, povm, expect)
+
+
+def _check_mle_variant(qp, n, povm, expect):
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
     rho = haar(n, 90 + n, rank=2 if n == 3 else None)
     tmg = qp.StateTomograph(qp.Qobj(rho))
     np.random.seed(n)
@@ -424,7 +443,71 @@ def test_state_tomograph_api(qp):
         qp.StateTomograph(qp.Qobj(rho), dst="nope")
 
 
-def test_tail_merging_is_bit_identical(qp, monkeypatch):
+def _pauli2_counts(qp, B, povm="proj", state_seed=5, seed=3):
+    rho = haar(2, state_seed)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(0)
+    tmg.experiment(10000, povm)
+    return tmg, tmg.sample_counts(B, 10000, povm, seed=seed)
+
+
+@pytest.mark.parametrize("povm", ["proj", "proj-set"])
+def test_pauli2_lane_mappings_are_bit_identical(qp, povm):
+    """k_mle_rrr_pauli2 evaluates ONE dataflow graph with two lane mappings (thread per sample in registers, warp
+    per sample with the products on DMMA).  Thread-only, warp-only and the production mix (hand-over of long-running
+    samples at several ages, with and without dedicated workers) must agree in every bit of every state and in
+    every iteration count; 'proj-set' has non-uniform guards (the second template instance)."""
+    from quantpy_b200 import _native as nt
+
+    tmg, counts = _pauli2_counts(qp, 40000, povm)
+    kw = dict(max_iter=400, tol=1e-6, return_iters=True)
+    with nt.option("MLE_LANES", 1):
+        a, ia = tmg.point_estimate_batch(counts, "mle", **kw)
+    with nt.option("MLE_LANES", 32):
+        b, ib = tmg.point_estimate_batch(counts, "mle", **kw)
+    assert np.array_equal(ia, ib) and np.array_equal(a, b)
+    assert ia.max() == 400 and ia.min() < 50
+    for age, live, workers in [(0, 0, 0), (1, 32, 4), (37, 3, -1), (150, 12, 2)]:
+        with nt.option("MLE_PARK_AGE", age), nt.option("MLE_PARK_LIVE", live), nt.option("MLE_W_WARPS", workers):
+            c, ic = tmg.point_estimate_batch(counts, "mle", **kw)
+        assert np.array_equal(ia, ic) and np.array_equal(a, c), (age, live, workers)
+    # init='mixed' (no start state) and a batch small enough to take the warp-only path on its own
+    with nt.option("MLE_LANES", 1):
+        a, ia = tmg.point_estimate_batch(counts[:3000], "mle", init="mixed", **kw)
+    c, ic = tmg.point_estimate_batch(counts[:3000], "mle", init="mixed", **kw)
+    assert np.array_equal(ia, ic) and np.array_equal(a, c)
+
+
+def test_pauli2_fused_distance_is_bit_identical(qp):
+    """The bootstrap's Hilbert-Schmidt distance comes out of the MLE kernel's write-back (both lane mappings) or out
+    of k_distance (NO_HS_FUSION): same formula, same `< 1e-15 -> 0` rule (quantpy/geometry.py:17-18), same bits."""
+    import torch
+
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    rho = haar(2, 5)
+    state = qp.Qobj(rho)
+    povm = qp.generate_measurement_matrix("proj", 2)
+    plan = engine.state_plan(povm, np.ones(1) * 10000)
+    probs = plan.probabilities(state.bloch)[0].contiguous()
+    kw = dict(method="mle", max_iter=300, tol=1e-6, dst="hs")
+    out = {}
+    for name, opts in {"fused": {}, "thread": {"MLE_LANES": 1}, "warp": {"MLE_LANES": 32}, "unfused": {"NO_HS_FUSION": 1}}.items():
+        import contextlib
+
+        with contextlib.ExitStack() as stack:
+            for k, v in opts.items():
+                stack.enter_context(nt.option(k, v))
+            got = plan.bootstrap(probs, 20000, 77, 0, rho, **kw)
+            torch.cuda.synchronize()
+            out[name] = (got["dist"].cpu().numpy(), got["iters"].cpu().numpy())
+    for name in ("thread", "warp", "unfused"):
+        assert np.array_equal(out["fused"][1], out[name][1]), name
+        assert np.array_equal(out["fused"][0], out[name][0]), name
+
+
+def test_tail_merging_is_bit_identical(qp):
     """The structured kernel hands a warp's last samples to its partner warp once the queue is empty; every
     sample still runs its own iteration sequence, so the output must not change by a single bit."""
     rho = haar(2, 5)
@@ -432,8 +515,10 @@ def test_tail_merging_is_bit_identical(qp, monkeypatch):
     np.random.seed(0)
     tmg.experiment(10000, "proj")
     counts = tmg.sample_counts(60000, 10000, "proj", seed=3)
+    from quantpy_b200 import _native as nt
+
     a, ia = tmg.point_estimate_batch(counts, "mle", max_iter=400, tol=1e-6, return_iters=True)
-    monkeypatch.setenv("QPB_NO_TAIL_MERGE", "1")
-    b, ib = tmg.point_estimate_batch(counts, "mle", max_iter=400, tol=1e-6, return_iters=True)
+    with nt.option("NO_TAIL_MERGE", 1):
+        b, ib = tmg.point_estimate_batch(counts, "mle", max_iter=400, tol=1e-6, return_iters=True)
     assert np.array_equal(ia, ib) and np.array_equal(a, b)
     assert ia.max() == 400 and ia.min() < 50
