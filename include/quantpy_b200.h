@@ -72,6 +72,9 @@ QPB_API void qpb_reset_launch_count(void);
 /* Roofline probe (bench.py only): runs a pure FP64 FMA kernel on every SM; *flops_out_host receives the
  * number of floating-point operations it performs so that the caller can time it with CUDA events. */
 QPB_API int qpb_fp64_fma_probe(int64_t iters_per_thread, double* sink, double* flops_out_host, void* stream);
+/* Shared-memory roofline probe (bench.py only): conflict-free 64-bit loads from every SM; *wavefronts_out_host
+ * receives the number of 128-byte shared-memory wavefronts it moves. */
+QPB_API int qpb_smem_probe(int64_t iters_per_thread, double* sink, double* wavefronts_out_host, void* stream);
 
 /* ---- state plan ---------------------------------------------------------------------------
  * Device-resident operator tables for one (POVM, shot vector) pair, hoisted out of the
@@ -199,6 +202,12 @@ QPB_API int qpb_mhmc_state(const qpb_state_plan* plan, int C, int n_samples, int
  * out = sorted(in) ascending, n float64 keys, in != out (`dist.sort()`, interval.py:610 / 683).  Keys only: the
  * quantile function needs the order statistics, not the permutation.                                   */
 QPB_API int qpb_sort_f64(long long n, const double* in, double* out, void* stream);
+/* Multi-GPU quantile step: every rank sorts its shard, ONE all-gather collects the sorted shards, and this call
+ * merges the n_runs (<= 64) ascending runs in[run_start[j] .. run_start[j] + run_len[j]) into `out` (ascending,
+ * sum of the lengths) -- the sorted array the reference gets from `dist.sort()` on the concatenation
+ * (interval.py:610, 683), without re-sorting world_size * shard keys on every rank.  in != out.            */
+QPB_API int qpb_merge_sorted_runs(int n_runs, const int32_t* run_len_host, const int64_t* run_start_host,
+                                  const double* in, double* out, void* stream);
 
 #ifdef __cplusplus
 }

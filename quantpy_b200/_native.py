@@ -36,6 +36,7 @@ SIGNATURES = {
     "qpb_set_option": (_int, [_int, _int]),
     "qpb_get_option": (_int, [_int]),
     "qpb_fp64_fma_probe": (_int, [ctypes.c_int64, _vp, ctypes.POINTER(_dbl), _vp]),
+    "qpb_smem_probe": (_int, [ctypes.c_int64, _vp, ctypes.POINTER(_dbl), _vp]),
     "qpb_state_plan_create": (_int, [ctypes.POINTER(_vp), _int, _int, _vp, _vp, _vp]),
     "qpb_state_plan_destroy": (_int, [_vp]),
     "qpb_povm_probs": (_int, [_int, _int, _int, _vp, _vp, _dbl, _int, _vp, _vp]),
@@ -53,6 +54,7 @@ SIGNATURES = {
     "qpb_polytope_confidence": (_int, [_int, _int, _int, _vp, _vp, _int, _vp, _vp, _vp]),
     "qpb_l2_moments": (_int, [_int, _int, _int, _vp, _vp, _dbl, _vp, _vp, _vp]),
     "qpb_sort_f64": (_int, [ctypes.c_longlong, _vp, _vp, _vp]),
+    "qpb_merge_sorted_runs": (_int, [_int, _vp, _vp, _vp, _vp, _vp]),
     "qpb_mhmc_state": (_int, [_vp, _int, _int, _int, _int, _dbl, _vp, _int, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp,
                               _vp]),
     "qpb_process_plan_create": (_int, [ctypes.POINTER(_vp), _int, _int, _int, _vp, _vp]),

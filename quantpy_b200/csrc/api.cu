@@ -123,9 +123,37 @@ __global__ void k_fp64_fma_probe(long iters, double seed, double* __restrict__ s
     const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (s == 12345.6789) sink[0] = s;  // never true; keeps the chains alive
 }
+// Shared-memory roofline probe: every warp streams conflict-free 64-bit loads (two 128-byte wavefronts per
+// warp instruction) from a 16 KB region; bench.py times it to get the device's wavefront rate.
+__global__ void __launch_bounds__(1024) k_smem_probe(long iters, double* __restrict__ sink) {
+    __shared__ double buf[2048];
+    for (int i = threadIdx.x; i < 2048; i += blockDim.x) buf[i] = (double)i;
+    __syncthreads();
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int idx = threadIdx.x;
+    for (long i = 0; i < iters; ++i) {
+        a0 += buf[idx & 2047];
+        a1 += buf[(idx + 512) & 2047];
+        a2 += buf[(idx + 1024) & 2047];
+        a3 += buf[(idx + 1536) & 2047];
+        idx += 32;
+    }
+    const double s = (a0 + a1) + (a2 + a3);
+    if (s == 12345.6789) sink[0] = s;
+}
 }  // namespace qpb
 
 extern "C" {
+
+int qpb_smem_probe(int64_t iters_per_thread, double* sink, double* wavefronts_out_host, void* stream) {
+    QPB_REQUIRE(iters_per_thread > 0 && sink != nullptr, "bad probe arguments");
+    const int blocks = qpb::num_sms() * 2, threads = 1024;
+    qpb::k_smem_probe<<<blocks, threads, 0, (cudaStream_t)stream>>>((long)iters_per_thread, sink);
+    QPB_LAUNCHED("k_smem_probe");
+    // 4 LDS.64 per thread-iteration = 4 warp instructions per warp-iteration, 2 wavefronts each
+    if (wavefronts_out_host) *wavefronts_out_host = 8.0 * (double)iters_per_thread * blocks * (threads / 32);
+    return QPB_OK;
+}
 
 int qpb_fp64_fma_probe(int64_t iters_per_thread, double* sink, double* flops_out_host, void* stream) {
     QPB_REQUIRE(iters_per_thread > 0 && sink != nullptr, "bad probe arguments");

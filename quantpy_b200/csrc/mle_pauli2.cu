@@ -132,21 +132,30 @@ __device__ __forceinline__ double flip(double x, unsigned neg) {  // neg ? -x : 
 
 // hs_dst(rho, ref) = sqrt(|Tr (rho - ref)^2|) / sqrt 2, no conjugate (quantpy/geometry.py:5-20), from the packed state
 __device__ __forceinline__ double hs_distance_packed(const double (&h)[16], const double* __restrict__ ref) {
-    double sr = 0.0, si = 0.0;
+    // term e = (a, b): (rho - ref)[a][b] (rho - ref)[b][a]; summed in the order of k_distance's warp butterfly
+    // (element e in lane e: partners e^8, e^4, e^2, e^1), so both paths give the same bits
+    double tr[16], ti[16];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const double har = a <= b ? h[a * 4 + b] : h[b * 4 + a];
             const double hai = a == b ? 0.0 : (a < b ? h[b * 4 + a] : -h[a * 4 + b]);
-            const double ur = dsub(har, __ldg(ref + 2 * (a * 4 + b)));
-            const double ui = dsub(hai, __ldg(ref + 2 * (a * 4 + b) + 1));
-            const double vr = dsub(har, __ldg(ref + 2 * (b * 4 + a)));        // Re (rho - ref)[b][a]
-            const double vi = dsub(-hai, __ldg(ref + 2 * (b * 4 + a) + 1));   // Im (rho - ref)[b][a]
-            sr = dadd(sr, dfma(-ui, vi, dmul(ur, vr)));
-            si = dadd(si, dfma(ui, vr, dmul(ur, vi)));
+            const double ur = har - __ldg(ref + 2 * (a * 4 + b));
+            const double ui = hai - __ldg(ref + 2 * (a * 4 + b) + 1);
+            const double vr = har - __ldg(ref + 2 * (b * 4 + a));        // Re (rho - ref)[b][a]
+            const double vi = -hai - __ldg(ref + 2 * (b * 4 + a) + 1);   // Im (rho - ref)[b][a]
+            tr[a * 4 + b] = dadd(0.0, dfma(-ui, vi, dmul(ur, vr)));
+            ti[a * 4 + b] = dadd(0.0, dfma(ui, vr, dmul(ur, vi)));
         }
-    const double v = sqrt(sqrt(dfma(si, si, dmul(sr, sr)))) / sqrt(2.0);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int e = 0; e < o; ++e) {
+            tr[e] = dadd(tr[e], tr[e + o]);
+            ti[e] = dadd(ti[e], ti[e + o]);
+        }
+    const double v = sqrt(sqrt(dfma(ti[0], ti[0], dmul(tr[0], tr[0])))) / sqrt(2.0);
     return v < kZeroBelow ? 0.0 : v;  // geometry.py:17-18
 }
 

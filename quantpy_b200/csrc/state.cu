@@ -425,12 +425,14 @@ __global__ void k_distance(int d, int B, const double* __restrict__ rho, const d
                 const int a = e / d, bb = e % d;
                 const cplx p = x[e], q = refc[e], pt = x[bb * d + a], qt = refc[bb * d + a];
                 const double ur = p.re - q.re, ui = p.im - q.im, vr = pt.re - qt.re, vi = pt.im - qt.im;
-                re += ur * vr - ui * vi;
-                im += ur * vi + ui * vr;
+                // explicit operations: the fused write-back of k_mle_rrr_pauli2 (hs_distance_packed) evaluates the
+                // same terms and the same butterfly tree, so fused and unfused bootstraps agree in every bit
+                re = __dadd_rn(re, __fma_rn(-ui, vi, __dmul_rn(ur, vr)));
+                im = __dadd_rn(im, __fma_rn(ui, vr, __dmul_rn(ur, vi)));
             }
             re = warp_sum(re);
             im = warp_sum(im);
-            val = sqrt(sqrt(re * re + im * im)) / sqrt(2.0);
+            val = sqrt(sqrt(__fma_rn(im, im, __dmul_rn(re, re)))) / sqrt(2.0);
         } else if (kind == QPB_DIST_TRACE) {
             for (int e = lane; e < dd; e += 32) {
                 const int a = e / d, bb = e % d;

@@ -325,17 +325,50 @@ def l2_moments(frequencies, n_trials, weights):
     return (float(m[0]), float(v[0])) if single else (m, v)
 
 
-_PLAN_CACHE = {}
+_PLAN_CACHE = {}      # content digest -> StatePlan
+_PLAN_BY_IDENTITY = {}  # (id(povm array), id(shots array)) -> (weak refs, cheap fingerprints, plan)
+
+
+def _fingerprint(a):
+    """Cheap change detector for an array whose identity we have seen: shape, strides, dtype, data pointer and
+    a strided sample of at most 64 values (a full hash of the 2.65 MB POVM tensor at n = 4 cost more than the
+    kernels of a 1000-sample interval)."""
+    flat = a.reshape(-1)
+    step = max(1, flat.size // 64)
+    return (a.shape, a.dtype.str, a.__array_interface__["data"][0], flat[::step][:64].tobytes())
 
 
 def state_plan(povm_matrix, n_measurements):
-    """Plans are cached by content so that repeated point_estimate calls reuse the uploaded tables."""
-    povm_matrix = np.ascontiguousarray(np.asarray(povm_matrix, dtype=np.float64))
+    """Plans are cached so that repeated point_estimate / setup calls reuse the uploaded tables.
+
+    Fast path: the same array OBJECTS as last time (the tomograph's `povm_matrix` / `n_measurements` attributes)
+    with unchanged fingerprints -> no hashing.  Slow path: content digest over both arrays (arrays rebuilt by
+    generate_measurement_matrix on every call still hit the cache)."""
+    import weakref
+
+    ident = None
+    if isinstance(povm_matrix, np.ndarray) and isinstance(n_measurements, np.ndarray):
+        ident = (id(povm_matrix), id(n_measurements))
+        hit = _PLAN_BY_IDENTITY.get(ident)
+        if hit is not None:
+            ref_p, ref_n, fp_p, fp_n, plan = hit
+            if ref_p() is povm_matrix and ref_n() is n_measurements and _fingerprint(povm_matrix) == fp_p \
+                    and _fingerprint(n_measurements) == fp_n:
+                return plan
+    pm = np.ascontiguousarray(np.asarray(povm_matrix, dtype=np.float64))
     n = np.ascontiguousarray(np.asarray(n_measurements, dtype=np.float64).reshape(-1))
-    key = (povm_matrix.shape, hashlib.blake2b(povm_matrix.tobytes() + n.tobytes(), digest_size=16).digest())
+    key = (pm.shape, hashlib.blake2b(pm.tobytes() + n.tobytes(), digest_size=16).digest())
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         if len(_PLAN_CACHE) >= 16:
             _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-        plan = _PLAN_CACHE[key] = StatePlan(povm_matrix, n)
+        plan = _PLAN_CACHE[key] = StatePlan(pm, n)
+    if ident is not None:
+        if len(_PLAN_BY_IDENTITY) >= 64:
+            _PLAN_BY_IDENTITY.clear()
+        try:
+            _PLAN_BY_IDENTITY[ident] = (weakref.ref(povm_matrix), weakref.ref(n_measurements),
+                                        _fingerprint(povm_matrix), _fingerprint(n_measurements), plan)
+        except TypeError:  # pragma: no cover  (array subclass without weakref support)
+            pass
     return plan

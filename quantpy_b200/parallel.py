@@ -46,21 +46,65 @@ def all_gather_concat(local, n_total):
     if size == 1:
         return local
     import torch
-    import torch.distributed as dist
 
-    width = -(-int(n_total) // size)
-    gathered = torch.empty((size * width,), dtype=local.dtype, device=local.device)
+    gathered, width = _all_gather_padded(local, n_total)
     if int(n_total) == size * width:  # equal shards: the gathered buffer already is the concatenation
-        dist.all_gather_into_tensor(gathered, local.contiguous())
         return gathered
-    padded = torch.zeros((width,), dtype=local.dtype, device=local.device)
-    padded[: local.numel()] = local
-    dist.all_gather_into_tensor(gathered, padded)
     pieces = []
     for r in range(size):
         lo, hi = shard_bounds(n_total, r, size)
         pieces.append(gathered[r * width: r * width + (hi - lo)])
     return torch.cat(pieces)
+
+
+def _all_gather_padded(local, n_total):
+    """ONE all_gather_into_tensor of every rank's shard, padded to the common width -> (buffer [size*width], width)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, size = world()
+    width = -(-int(n_total) // size)
+    gathered = torch.empty((size * width,), dtype=local.dtype, device=local.device)
+    if local.numel() == width:
+        dist.all_gather_into_tensor(gathered, local.contiguous())
+    else:
+        padded = torch.zeros((width,), dtype=local.dtype, device=local.device)
+        padded[: local.numel()] = local
+        dist.all_gather_into_tensor(gathered, padded)
+    return gathered, width
+
+
+def gather_sorted(local, n_total):
+    """The sorted vector of all ranks' values (what the reference gets from `dist.sort()`, interval.py:610): every
+    rank sorts its own shard, ONE all-gather collects the sorted shards, and a counting merge of the world_size
+    runs (qpb_merge_sorted_runs, one launch) replaces a second full sort on every rank.  CUDA tensors only; the
+    CPU (gloo) path used by the host-logic tests sorts the concatenation."""
+    rank, size = world()
+    if not local.is_cuda:
+        import torch
+
+        return torch.sort(all_gather_concat(local, n_total)).values
+    import ctypes
+
+    import torch
+
+    from . import _native as nt
+    from . import engine
+
+    mine = engine.sort_f64(local)
+    if size == 1:
+        return mine
+    gathered, width = _all_gather_padded(mine, n_total)
+    lens = np.zeros(size, dtype=np.int32)
+    starts = np.zeros(size, dtype=np.int64)
+    for r in range(size):
+        lo, hi = shard_bounds(n_total, r, size)
+        lens[r], starts[r] = hi - lo, r * width
+    out = torch.empty((int(n_total),), dtype=local.dtype, device=local.device)
+    nt.check(nt.load_library().qpb_merge_sorted_runs(size, lens.ctypes.data_as(ctypes.c_void_p),
+                                                     starts.ctypes.data_as(ctypes.c_void_p), nt.ptr(gathered),
+                                                     nt.ptr(out), nt.stream_ptr()))
+    return out
 
 
 # bytes that crossed PCIe through this module since import (bench.py reads the difference around a call)

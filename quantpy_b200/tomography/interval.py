@@ -57,9 +57,8 @@ class ConfidenceInterval(ABC):
 
     def _finish(self, local_dist, n_points):
         """All-gather the per-rank distances, keep them (sorted) and build the quantile function."""
-        full = parallel.all_gather_concat(local_dist, n_points)
         # sorted on the device and left there: the quantile function fetches what a call needs, `dist` the rest
-        self.cl_to_dist = parallel.quantile_function(full)
+        self.cl_to_dist = parallel.quantile_function(parallel.gather_sorted(local_dist, n_points), presorted=True)
 
     @property
     def dist(self):
@@ -215,7 +214,9 @@ class BootstrapProcessInterval(ConfidenceInterval):
     def __init__(self, tmg, n_points=1000, method="lifp", cptp=True, tol=1e-10, channel=None,
                  states_est_method="lin", states_physical=True, states_init="lin"):
         """Parametric bootstrap around `channel` (default: the tomograph's reconstructed channel);
-        kwargs as ProcessTomograph.point_estimate."""
+        kwargs as ProcessTomograph.point_estimate.  Supported for n_qubits <= 2 (see ProcessTomograph.sample_counts).
+        Deviation from the reference: with method='states' the replicas use `states_est_method` (the reference's
+        loop never forwards it, quantpy/tomography/interval.py:676-681, so it always bootstraps with 'lin')."""
         super().__init__(tmg, **_pop_hidden_keys(locals()))
 
     def setup(self, seed=None):
@@ -234,32 +235,25 @@ class BootstrapProcessInterval(ConfidenceInterval):
         seed = parallel.broadcast_seed(engine.next_seed()) if seed is None else int(seed)
         first = self.tmg.tomographs[0]
         boot = self.tmg.__class__(self.channel, self.tmg.input_states, self.tmg.dst)
+        boot.adopt_measurement(first.povm_matrix, first.n_measurements)  # tables only: no sampling, no RNG draw
         centre = self.channel.choi.matrix
         kind = dst_kind(self.tmg.dst)
         torch = nt.torch_cuda()
+        counts = boot.sample_counts(hi - lo, first.n_measurements, first.povm_matrix, seed, lo, device=True)
         if self.method == "lifp":
-            counts = boot.sample_counts(hi - lo, first.n_measurements, first.povm_matrix, seed, lo, device=True)
-            boot.experiment(first.n_measurements, first.povm_matrix)  # gives boot its POVM / shot bookkeeping
             choi = boot.point_estimate_batch(counts, cptp=self.cptp, device=True)
-            if kind is not None:
-                local = engine.distance(choi, centre, kind)
-            else:
-                from ..qobj import Qobj
-
-                local = torch.tensor([float(self.tmg.dst(Qobj(c), self.channel.choi))
-                                      for c in nt.complex_to_host(choi)], dtype=torch.float64, device="cuda")
         else:
-            counts = boot.sample_counts(hi - lo, first.n_measurements, first.povm_matrix, seed, lo, device=True)
-            boot.experiment(first.n_measurements, first.povm_matrix)
+            # the reference's bootstrap forwards only states_physical / states_init (interval.py:676-681), so its
+            # replicas always use the default states_est_method='lin'; here the constructor's value is honoured
             choi = boot.point_estimate_states_batch(counts, cptp=self.cptp, method=self.states_est_method,
                                                     physical=self.states_physical, init=self.states_init, device=True)
-            if kind is not None:
-                local = engine.distance(choi, centre, kind)
-            else:
-                from ..qobj import Qobj
+        if kind is not None:
+            local = engine.distance(choi, centre, kind)
+        else:
+            from ..qobj import Qobj
 
-                local = torch.tensor([float(self.tmg.dst(Qobj(c), self.channel.choi))
-                                      for c in nt.complex_to_host(choi)], dtype=torch.float64, device="cuda")
+            local = torch.tensor([float(self.tmg.dst(Qobj(c), self.channel.choi))
+                                  for c in nt.complex_to_host(choi)], dtype=torch.float64, device="cuda")
         self._finish(local, self.n_points)
 
 

@@ -61,8 +61,25 @@ class ProcessTomograph:
         for tmg in self.tomographs:
             tmg.experiment(n_measurements, povm, warm_start=warm_start)
 
+    def adopt_measurement(self, povm_matrix, n_measurements):
+        """Give this tomograph the POVM / shot bookkeeping of an experiment WITHOUT sampling one: the bootstrap
+        intervals reconstruct batches of count tables with `point_estimate_batch` and only need the tables."""
+        povm_matrix = np.asarray(povm_matrix, dtype=np.float64)
+        shots = np.asarray(n_measurements)
+        self.tomographs = []
+        for out in self._output_states():
+            tmg = StateTomograph(out)
+            tmg.povm_matrix = povm_matrix
+            tmg.results = np.zeros(povm_matrix.shape[:2], dtype=np.int64)
+            tmg.n_measurements = shots
+            self.tomographs.append(tmg)
+
     def sample_counts(self, n_samples, n_measurements, povm="proj-set", seed=None, offset=0, device=False):
         """`n_samples` simulated process tomographies at once -> counts [n_samples, S, P, O].
+
+        Limits of the process path: n_qubits <= 2 (S*P <= 256 multinomials per replica in one launch;
+        the reference takes 0.85 s per 2-qubit estimate and is not usable beyond that either).
+
 
         All S output states are sampled by one kernel launch: the (state, POVM) pairs are presented to
         the sampler as S*P independent multinomials."""
@@ -75,6 +92,9 @@ class ProcessTomograph:
             raise ValueError("Wrong length for argument `n_measurements`")
         outs = self._output_states()
         S = len(outs)
+        if S * P > 256:
+            raise ValueError(f"process tomography with {S} input states x {P} POVMs exceeds the 256 multinomials "
+                             "per replica the sampler takes in one launch (supported: n_qubits <= 2)")
         plan = engine.state_plan(povm_matrix, shots)
         probs = plan.probabilities(np.array([o.bloch for o in outs]))  # [S, K]
         shots_all = np.tile(np.rint(np.asarray(shots, dtype=np.float64)).astype(np.int32), S)

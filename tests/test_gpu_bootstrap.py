@@ -340,3 +340,44 @@ def test_process_states_method_batched(qp, golden, n, method):
                                       channel=tmg.channel)
     itv.setup(seed=1)
     assert itv.dist.shape == (300,) and np.all(np.diff(itv.dist) >= 0) and itv.dist[0] > 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 1000, 4097, 12500, 16384, 16385, 100000])
+def test_sort_kernels_match_numpy(qp, n):
+    """qpb_sort_f64: shared-memory bitonic network up to 16384 keys, device radix sort above; keys only, bit-exact."""
+    import torch
+
+    from quantpy_b200 import engine
+
+    rng = np.random.default_rng(n)
+    x = rng.random(n)
+    x[: n // 7] = x[n // 5: n // 5 + n // 7]  # ties
+    got = engine.sort_f64(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert np.array_equal(got, np.sort(x))
+
+
+@pytest.mark.parametrize("lens", [[5], [4, 3], [12500] * 8, [100000, 99999, 1, 0, 7], [0, 0, 3]])
+def test_merge_sorted_runs_is_the_sorted_concatenation(qp, lens):
+    """qpb_merge_sorted_runs (the multi-GPU quantile step): padded, individually sorted shards -> the bit-exact
+    `dist.sort()` of their concatenation (interval.py:610), including ties across runs."""
+    import ctypes
+
+    import torch
+
+    from quantpy_b200 import _native as nt
+
+    rng = np.random.default_rng(len(lens))
+    width = max(max(lens), 1)
+    runs = [np.sort(np.round(rng.random(m), 3)) for m in lens]  # rounding makes cross-run ties common
+    buf = np.full(len(lens) * width, -1.0)
+    for r, run in enumerate(runs):
+        buf[r * width: r * width + len(run)] = run
+    total = int(sum(lens))
+    dev = torch.from_numpy(buf).cuda()
+    out = torch.full((total,), np.nan, dtype=torch.float64, device="cuda")
+    ln = np.asarray(lens, dtype=np.int32)
+    st = np.arange(len(lens), dtype=np.int64) * width
+    nt.check(nt.load_library().qpb_merge_sorted_runs(len(lens), ln.ctypes.data_as(ctypes.c_void_p),
+                                                     st.ctypes.data_as(ctypes.c_void_p), nt.ptr(dev), nt.ptr(out),
+                                                     nt.stream_ptr()))
+    assert np.array_equal(out.cpu().numpy(), np.sort(np.concatenate(runs)))

@@ -272,6 +272,56 @@ def test_mle_tolerance_mode_matches_oracle(qp, n, povm, B, tol, max_iter):
     assert same.mean() > 0.999  # a step norm within rounding of tol may stop one iteration apart
     assert fro(got[same], want[same]).max() < 1e-10
     assert 1 <= its.mean() < max_iter
+    _check_off_by_one(tmg, counts, got, its, wits)
+
+
+def _check_off_by_one(tmg, counts, got, its, wits):
+    """Samples whose stopping iteration differs from the oracle's (step norm within rounding of tol) must differ by
+    exactly one iteration and equal the oracle's iterate at the kernel's own count to 1e-10."""
+    for i in np.flatnonzero(its != wits):
+        assert abs(int(its[i]) - int(wits[i])) == 1, (i, its[i], wits[i])
+        step = ostate.mle_rrr(counts[i: i + 1], tmg.povm_matrix, tmg.n_measurements, max_iter=int(its[i]), tol=0.0)
+        assert fro(got[i: i + 1], step).max() < 1e-10
+
+
+def test_mle_bench_setting_stragglers_match_oracle(qp):
+    """The exact bench.py setting (BASELINE configs[1]: 2 qubits, 'proj', 1e4 shots, B = 1e5, tol 1e-6, max_iter 1000),
+    where long-running samples change lane mapping mid-flight: the 200 longest-running samples and a 1 % stride
+    are re-derived by the oracle -- same iteration counts (or one apart, checked at one-step distance), states 1e-10."""
+    rho = haar(2, 0)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(0)
+    tmg.experiment(10000, "proj")
+    B = 100000
+    counts = tmg.sample_counts(B, 10000, "proj", seed=1234)
+    got, its = tmg.point_estimate_batch(counts, "mle", max_iter=1000, tol=1e-6, return_iters=True)
+    assert its.max() > 600 and its.mean() > 100
+    pick = np.unique(np.concatenate([np.argsort(-its)[:200], np.arange(0, B, 100)]))
+    want, wits = ostate.mle_rrr(counts[pick], tmg.povm_matrix, tmg.n_measurements, max_iter=1000, tol=1e-6,
+                                return_iters=True)
+    same = its[pick] == wits
+    assert same.mean() > 0.995
+    assert fro(got[pick][same], want[same]).max() < 1e-10
+    _check_off_by_one(tmg, counts[pick], got[pick], its[pick], wits)
+
+
+def test_mle_four_qubits_deep_iterations_match_oracle(qp):
+    """k_mle_rrr_axis<4> at the depth the bench runs it: 200 iterations on 32 count tables, a quarter of them
+    drawn from a rank-1 state (zero counts, probabilities at the 1e-10 guard) -- DMMA accumulation order and
+    the axis maps stay within 1e-10 of the dense oracle."""
+    full, pure = haar(4, 11), haar(4, 12, rank=1)
+    povm = qp.generate_measurement_matrix("proj", 4)
+    tables = []
+    for state, m, seed in ((full, 24, 1), (pure, 8, 2)):
+        tmg = qp.StateTomograph(qp.Qobj(state))
+        np.random.seed(seed)
+        tmg.experiment(10000, "proj")
+        tables.append(tmg.sample_counts(m, 10000, "proj", seed=seed))
+    counts = np.concatenate(tables)
+    got, its = tmg.point_estimate_batch(counts, "mle", max_iter=200, tol=0.0, return_iters=True)
+    want = ostate.mle_rrr(counts, povm, np.ones(1) * 10000, max_iter=200, tol=0.0)
+    assert (its == 200).all()
+    assert fro(got, want).max() < 1e-10
 
 
 @pytest.mark.parametrize("n,povm,disable,expect", [

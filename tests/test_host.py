@@ -198,6 +198,10 @@ full = parallel.all_gather_concat(local, n)
 assert torch.equal(full, torch.arange(n, dtype=torch.float64) * 0.5 + 1234), full
 q = parallel.quantile_function(full.numpy()[::-1])
 assert np.isclose(q(0.0), 1234.0) and np.isclose(q(1.0), 1239.0) and np.isclose(q(0.5), 1236.5)
+# the interval's own path: every rank contributes an unsorted shard, all get the globally sorted vector
+mixed = torch.tensor([((7 * i) % 11) * 0.25 for i in range(lo, hi)], dtype=torch.float64)
+merged = parallel.gather_sorted(mixed, n)
+assert torch.equal(merged, torch.sort(torch.tensor([((7 * i) % 11) * 0.25 for i in range(n)], dtype=torch.float64)).values)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
