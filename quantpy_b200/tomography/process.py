@@ -22,6 +22,9 @@ from ..routines import _left_inv, _out_ptrace_oper, generate_pauli, generate_sin
 from .state import StateTomograph, resolve_dst
 
 
+_LIFP_CACHE = {}  # (n, POVM table, input basis) -> (lifp operator, its left inverse, device plan)
+
+
 def _generate_input_states(input_states, n_qubits):
     """Named sets are the Bloch rows of the POVM of that name, normalised to unit trace (process.py:330-339)."""
     if isinstance(input_states, list):
@@ -120,18 +123,25 @@ class ProcessTomograph:
         return engine.weighted_povm(first.povm_matrix, first.n_measurements)
 
     def _process_plan(self):
-        """Build (once per POVM/shots) the lifp operator of process.py:197-209 and upload its left inverse."""
+        """Build (once per input basis / POVM / shots, shared by every tomograph of the process) the lifp operator
+        of process.py:197-209 and upload its left inverse.  The reference rebuilds both on every point_estimate; a
+        bootstrap interval creates a fresh tomograph per call, so the cache lives at module level."""
         A = self._weighted_povm()
-        key = A.tobytes()
+        rho_t = np.array([state.matrix.T for state in self.input_basis.elements])
+        key = (self.channel.n_qubits, A.shape, A.tobytes(), rho_t.tobytes())
         if self._plan_key != key:
-            n = self.channel.n_qubits
-            d = 2**n
-            E = np.tensordot(A, generate_pauli(n), axes=1)  # (K, d, d) POVM operators
-            rho_t = np.array([state.matrix.T for state in self.input_basis.elements])
-            # row(s, k) = vec(rho_s (x) E_k^T) = (rho_s^T (x) E_k) flattened row-major
-            self._lifp_oper = np.einsum("sij,kab->skiajb", rho_t, E).reshape(len(rho_t) * len(E), d**4)
-            self._lifp_oper_inv = _left_inv(self._lifp_oper)
-            self._plan = engine.ProcessPlan(n, self._lifp_oper_inv, len(rho_t), len(E))
+            hit = _LIFP_CACHE.get(key)
+            if hit is None:
+                n = self.channel.n_qubits
+                d = 2**n
+                E = np.tensordot(A, generate_pauli(n), axes=1)  # (K, d, d) POVM operators
+                # row(s, k) = vec(rho_s (x) E_k^T) = (rho_s^T (x) E_k) flattened row-major
+                oper = np.einsum("sij,kab->skiajb", rho_t, E).reshape(len(rho_t) * len(E), d**4)
+                inv = _left_inv(oper)
+                if len(_LIFP_CACHE) >= 8:
+                    _LIFP_CACHE.pop(next(iter(_LIFP_CACHE)))
+                hit = _LIFP_CACHE[key] = (oper, inv, engine.ProcessPlan(n, inv, len(rho_t), len(E)))
+            self._lifp_oper, self._lifp_oper_inv, self._plan = hit
             self._plan_key = key
         return self._plan
 
