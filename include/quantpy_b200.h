@@ -62,7 +62,8 @@ enum {
     QPB_OPT_MLE_PARK_LIVE = 14,  /* pauli2 MLE tuning: a drained warp with at most this many live samples hands them all over (0 = default) */
     QPB_OPT_MLE_W_WARPS = 15,    /* pauli2 MLE tuning: warp-per-sample workers per CTA from the start (0 = default, -1 = none) */
     QPB_OPT_MLE_PARK_PLATEAU = 16, /* pauli2 MLE tuning: first iteration count at which a non-decreasing step norm hands a sample over (0 = default, -1 = never) */
-    QPB_OPT_COUNT_ = 17
+    QPB_OPT_NO_TMA_GEMM = 17,      /* counts GEMM: plain tiled DMMA kernel instead of the TMA/mbarrier pipeline */
+    QPB_OPT_COUNT_ = 18
 };
 QPB_API int qpb_set_option(int which, int value);
 QPB_API int qpb_get_option(int which);

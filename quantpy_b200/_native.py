@@ -68,7 +68,7 @@ SIGNATURES = {
 OPTIONS = {"NO_TAIL_MERGE": 0, "NO_HS_FUSION": 1, "NO_PAULI_KERNEL": 2, "NO_CONST_KERNEL": 3, "NO_AXIS_KERNEL": 4,
            "NO_DMMA_GEMM": 5, "NO_ROW_JACOBI": 6, "NO_PACKED_JACOBI": 7, "NO_LIN_SMALL": 8, "SAMPLER": 9,
            "MLE_BLOCKS_PER_SM": 10, "MLE_LANES": 11, "NO_TILED_MLE": 12, "MLE_PARK_AGE": 13, "MLE_PARK_LIVE": 14,
-           "MLE_W_WARPS": 15, "MLE_PARK_PLATEAU": 16}
+           "MLE_W_WARPS": 15, "MLE_PARK_PLATEAU": 16, "NO_TMA_GEMM": 17}
 SAMPLERS = {"auto": 0, "alias": 1, "binomial": 2}
 
 

@@ -91,14 +91,14 @@ static const char* const kOptionEnv[QPB_OPT_COUNT_] = {
     "QPB_NO_TAIL_MERGE", "QPB_NO_HS_FUSION", "QPB_NO_PAULI_KERNEL", "QPB_NO_CONST_KERNEL", "QPB_NO_AXIS_KERNEL",
     "QPB_NO_DMMA_GEMM",  "QPB_NO_ROW_JACOBI", "QPB_NO_PACKED_JACOBI", "QPB_NO_LIN_SMALL",  "QPB_SAMPLER",
     "QPB_MLE_BLOCKS_PER_SM", "QPB_MLE_LANES", "QPB_NO_TILED_MLE",
-    "QPB_MLE_PARK_AGE", "QPB_MLE_PARK_LIVE", "QPB_MLE_W_WARPS", "QPB_MLE_PARK_PLATEAU"};
+    "QPB_MLE_PARK_AGE", "QPB_MLE_PARK_LIVE", "QPB_MLE_W_WARPS", "QPB_MLE_PARK_PLATEAU", "QPB_NO_TMA_GEMM"};
 static const bool g_options_loaded = [] {
     for (int i = 0; i < QPB_OPT_COUNT_; ++i) {
-        const char* e = getenv(kOptionEnv[i]);
+        const char* e = kOptionEnv[i] ? getenv(kOptionEnv[i]) : nullptr;
         int v = 0;
         if (e && *e) {
             if (i == QPB_OPT_SAMPLER) v = !strcmp(e, "alias") ? 1 : (!strcmp(e, "binomial") ? 2 : 0);
-            else if (i >= QPB_OPT_MLE_BLOCKS_PER_SM && i != QPB_OPT_NO_TILED_MLE) v = atoi(e);
+            else if (i >= QPB_OPT_MLE_BLOCKS_PER_SM && i != QPB_OPT_NO_TILED_MLE && i != QPB_OPT_NO_TMA_GEMM) v = atoi(e);
             else v = 1;
         }
         g_options[i].store(v);

@@ -6,8 +6,10 @@
 // one-warp-per-sample kernels had to stream the whole table from L2 for every sample.
 //
 // Tiling: CTA = 64 x 64 outputs, 8 warps in a 4 x 2 grid, warp tile 16 x 32 = 2 x 4 DMMA tiles
-// (mma.sync.aligned.m8n8k4 f64, FP64 accumulate), K step 16 through padded shared-memory tiles.
-// tcgen05 has no f64 kind, so DMMA via mma.sync is the FP64 tensor path on sm_100a.
+// (mma.sync.aligned.m8n8k4 f64, FP64 accumulate).  tcgen05 has no f64 kind, so DMMA via mma.sync is the FP64
+// tensor path on sm_100a.  Two kernels: k_gemm_counts_dmma (production: persistent, warp-specialised, operands
+// staged by TMA bulk copies into a 3-stage mbarrier ring) and k_gemm_counts_simple (load / barrier / compute,
+// for shapes whose rows are not 16-byte multiples, and as the cross-check of the pipeline).
 #include "../../include/quantpy_b200.h"
 #include "common.cuh"
 #include "plan.h"
@@ -40,7 +42,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 }
 
 __global__ void __launch_bounds__(256)
-k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ counts,
+k_gemm_counts_simple(int M, int N, int Ktot, int G, const int32_t* __restrict__ counts,
                    const double* __restrict__ inv_tot, const double* __restrict__ T, double* __restrict__ C) {
     __shared__ double As[GM * AS];
     __shared__ double Bs[GK * BS];
@@ -74,11 +76,14 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < GK; kk += 4) {
+            // k order inside a block of 16: step s takes k = 4 c + s from lane column c (the order in which the
+            // pipelined kernel's 16-byte count loads deliver them), so both kernels accumulate identically
+            const int kcol = 4 * (lane & 3) + (kk >> 2);
             double a[2], b[4];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) a[i] = As[(wm * 16 + i * 8 + (lane >> 2)) * AS + kk + (lane & 3)];
+            for (int i = 0; i < 2; ++i) a[i] = As[(wm * 16 + i * 8 + (lane >> 2)) * AS + kcol];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[(kk + (lane & 3)) * BS + wn * 32 + j * 8 + (lane >> 2)];
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kcol * BS + wn * 32 + j * 8 + (lane >> 2)];
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -102,6 +107,186 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
         }
 }
 
+// ---- pipelined kernel -------------------------------------------------------------------------------------------
+// Warp-specialised: warp 8 is the producer, warps 0-7 consume.
+//  * table operand (T): the producer streams K-chunks of 32 rows x 64 columns into a 4-stage shared-memory ring with
+//    TMA bulk copies (cp.async.bulk, SASS UBLKCP), one 512-byte row per copy, each landing at a padded row stride
+//    (68 doubles) that makes the DMMA fragment loads bank-conflict free; an mbarrier per stage counts the bytes in
+//    (full) and the consumer warps out (empty).
+//  * count operand: never staged.  A lane's fragment elements for four consecutive k-steps are one aligned 16-byte
+//    global load (k = 16 t + 4 c + s for step s, lane column c), converted and normalised in registers
+//    ((double)c * inv_total) on the way into the DMMA and prefetched one block of 16 ahead.  (A first version staged
+//    the counts by TMA as well: 64 row copies of 128 B per chunk made the single producer warp the bottleneck --
+//    46 % of the stall samples were consumers waiting on the full barrier, profiles/README_r2.md.)
+// CTAs are persistent over (m, n) tiles, n fastest, so the N tiles of one block of count rows run back to back and
+// re-read it from L1/L2.
+constexpr int KC = 32, STAGES = 4;
+constexpr int B_LD = GN + 4;  // doubles per table row in smem: a half-warp's 4 rows x 4 columns hit 16 distinct bank pairs
+struct GemmStage {
+    double b[KC * B_LD];
+};
+constexpr int kGemmConsumers = 8;
+constexpr int kGemmThreads = 32 * (kGemmConsumers + 1);
+constexpr size_t kGemmSmem = sizeof(GemmStage) * STAGES + sizeof(uint64_t) * 2 * STAGES;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ int4 ldg_counts4(const int32_t* p, bool ok) {
+    int4 v = make_int4(0, 0, 0, 0);
+    if (ok) asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+template <bool ONE_GROUP>
+__global__ void __launch_bounds__(kGemmThreads, 2)
+k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ counts,
+                   const double* __restrict__ inv_tot, const double* __restrict__ T, double* __restrict__ C) {
+    extern __shared__ __align__(128) unsigned char gsm[];
+    GemmStage* stages = reinterpret_cast<GemmStage*>(gsm);
+    uint64_t* full = reinterpret_cast<uint64_t*>(gsm + sizeof(GemmStage) * STAGES);
+    uint64_t* empty = full + STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles_n = (N + GN - 1) / GN, tiles_m = (M + GM - 1) / GM;
+    const long tiles = (long)tiles_m * tiles_n;
+    const int chunks = (Ktot + KC - 1) / KC;
+    const int ng = Ktot / G;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kGemmConsumers);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kGemmConsumers) {
+        // ---------------- producer: table rows by TMA ----------------
+        long it = 0;
+        for (long t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const int n0 = (int)(t % tiles_n) * GN;
+            const int cols = min(GN, N - n0);
+            for (int c = 0; c < chunks; ++c, ++it) {
+                const int s = (int)(it % STAGES);
+                const unsigned par = (unsigned)((it / STAGES) & 1);
+                const int k0 = c * KC, kc = min(KC, Ktot - k0);
+                mbar_wait(&empty[s], par ^ 1u);
+                if (lane == 0) mbar_expect_tx(&full[s], (unsigned)(kc * cols * 8));
+                __syncwarp();
+                // table row k = 16 h + 4 c + s goes to ring row 16 h + 4 s + c: the four lanes of a k-step (c = 0..3)
+                // then read four CONSECUTIVE padded rows, i.e. 16 distinct bank pairs per half-warp
+                if (lane < kc)
+                    tma_bulk_g2s(&stages[s].b[((lane & 16) + 4 * (lane & 3) + ((lane >> 2) & 3)) * B_LD],
+                                 T + (long)(k0 + lane) * N + n0, (unsigned)(cols * 8), &full[s]);
+            }
+        }
+        return;
+    }
+    // ---------------- consumers: 4 x 2 warps, warp tile 16 x 32 = 2 x 4 DMMA tiles ----------------
+    const int wm = warp >> 1, wn = warp & 1;
+    const int c4 = 4 * (lane & 3);
+    const int nblk = (Ktot + 15) >> 4;
+    long it = 0;
+    for (long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int m0 = (int)(t / tiles_n) * GM, n0 = (int)(t % tiles_n) * GN;
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const int r0 = wm * 16 + (lane >> 2);                              // tile rows r0 and r0 + 8 of this lane
+        const long g0 = min((long)m0 + r0, (long)M - 1), g1 = min((long)m0 + r0 + 8, (long)M - 1);
+        const int32_t* row0 = counts + g0 * Ktot + c4;
+        const int32_t* row1 = counts + g1 * Ktot + c4;
+        double inv0 = 0.0, inv1 = 0.0;
+        if (ONE_GROUP) {
+            inv0 = inv_tot[g0];
+            inv1 = inv_tot[g1];
+        }
+        int4 cur0 = ldg_counts4(row0, c4 + 3 < Ktot), cur1 = ldg_counts4(row1, c4 + 3 < Ktot);
+        for (int c = 0; c < chunks; ++c, ++it) {
+            const int s = (int)(it % STAGES);
+            mbar_wait(&full[s], (unsigned)((it / STAGES) & 1));
+            const double* bt = stages[s].b + wn * 32 + (lane >> 2);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int blk = 2 * c + half;
+                if (blk < nblk) {
+                    const int kb = blk * 16;                                // first k of this block
+                    const bool more = kb + 16 + c4 + 3 < Ktot;
+                    const int4 nxt0 = ldg_counts4(row0 + kb + 16, more), nxt1 = ldg_counts4(row1 + kb + 16, more);
+                    const bool okk = kb + c4 + 3 < Ktot;                    // this lane's four k of the block exist
+                    const int cc0[4] = {cur0.x, cur0.y, cur0.z, cur0.w}, cc1[4] = {cur1.x, cur1.y, cur1.z, cur1.w};
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        double a0 = (double)cc0[st], a1 = (double)cc1[st];
+                        if (ONE_GROUP) {
+                            a0 *= inv0;
+                            a1 *= inv1;
+                        } else {
+                            const int grp = okk ? (kb + c4 + st) / G : 0;
+                            a0 *= inv_tot[g0 * ng + grp];
+                            a1 *= inv_tot[g1 * ng + grp];
+                        }
+                        const double* brow = bt + (half * 16 + 4 * st + (lane & 3)) * B_LD;
+                        double b[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) b[j] = okk ? brow[j * 8] : 0.0;  // rows past Ktot hold stale bytes
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            dmma_m8n8k4(acc[0][j][0], acc[0][j][1], a0, b[j]);
+                            dmma_m8n8k4(acc[1][j][0], acc[1][j][1], a1, b[j]);
+                        }
+                    }
+                    cur0 = nxt0;
+                    cur1 = nxt1;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int m = m0 + wm * 16 + i * 8 + (lane >> 2);
+                const int n = n0 + wn * 32 + j * 8 + 2 * (lane & 3);
+                if (m < M) {
+                    if (n + 1 < N) {
+                        *reinterpret_cast<double2*>(C + (long)m * N + n) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    } else if (n < N) {
+                        C[(long)m * N + n] = acc[i][j][0];
+                    }
+                }
+            }
+    }
+}
+
 // C [M][N] = normalised(counts [M][Ktot]) * T [Ktot][N]; N must be even (packed outputs always are).
 int launch_gemm_counts(int M, int N, int Ktot, int G, const int32_t* counts, const double* T, double* C,
                        cudaStream_t st) {
@@ -112,8 +297,21 @@ int launch_gemm_counts(int M, int N, int Ktot, int G, const int32_t* counts, con
     const long items = (long)M * ng;
     k_group_inverse_totals<<<(int)((items + 7) / 8), 256, 0, st>>>(M, Ktot, G, counts, inv_tot);
     QPB_LAUNCHED("k_group_inverse_totals");
-    dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
-    k_gemm_counts_dmma<<<grid, 256, 0, st>>>(M, N, Ktot, G, counts, inv_tot, T, C);
+    // TMA bulk copies need 16-byte rows: Ktot % 4 == 0 and N even hold for every table on the path (6^n, 4^n,
+    // S*K with n >= 2 ...); anything else takes the plain tiled kernel
+    const bool aligned16 = (Ktot % 4) == 0 && (N % 2) == 0 && ((uintptr_t)counts % 16) == 0 && ((uintptr_t)T % 16) == 0;
+    if (!aligned16 || option(QPB_OPT_NO_TMA_GEMM)) {
+        dim3 grid((N + GN - 1) / GN, (M + GM - 1) / GM);
+        k_gemm_counts_simple<<<grid, 256, 0, st>>>(M, N, Ktot, G, counts, inv_tot, T, C);
+        QPB_LAUNCHED("k_gemm_counts_simple");
+        return QPB_OK;
+    }
+    const long tiles = (long)((N + GN - 1) / GN) * ((M + GM - 1) / GM);
+    long blocks = (long)num_sms() * 2;
+    if (blocks > tiles) blocks = tiles;
+    auto kern = ng == 1 ? k_gemm_counts_dmma<true> : k_gemm_counts_dmma<false>;
+    QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    kern<<<(int)blocks, kGemmThreads, kGemmSmem, st>>>(M, N, Ktot, G, counts, inv_tot, T, C);
     QPB_LAUNCHED("k_gemm_counts_dmma");
     return QPB_OK;
 }

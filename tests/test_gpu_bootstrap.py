@@ -381,3 +381,31 @@ def test_merge_sorted_runs_is_the_sorted_concatenation(qp, lens):
                                                      st.ctypes.data_as(ctypes.c_void_p), nt.ptr(dev), nt.ptr(out),
                                                      nt.stream_ptr()))
     assert np.array_equal(out.cpu().numpy(), np.sort(np.concatenate(runs)))
+
+
+def test_tma_pipelined_gemm_equals_plain_gemm(qp):
+    """k_gemm_counts_dmma (TMA bulk copies into a 3-stage mbarrier ring, persistent CTAs) against k_gemm_counts_simple:
+    same DMMA accumulation order, so linear inversion (n = 3, 4: M, K tails) and 'lifp' (grouped normalisation,
+    N = 32 and 512) must agree in every bit; both are separately held to 1e-10 against the oracle elsewhere."""
+    import torch
+
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    for n, B in ((3, 1000 + 37), (4, 130)):
+        rho, pm, plan, probs = _plan_for(qp, n, "proj", 20 + n)
+        counts = plan.sample(probs, B, 9, 0)
+        a = plan.lin(counts, False).cpu().numpy()
+        with nt.option("NO_TMA_GEMM", 1):
+            b = plan.lin(counts, False).cpu().numpy()
+        assert np.array_equal(a, b), n
+    for n, B in ((1, 333), (2, 70)):
+        chan = qp.channel.depolarizing(0.1, n)
+        tmg = qp.ProcessTomograph(chan, "sic")
+        np.random.seed(n)
+        tmg.experiment(10000, "proj-set")
+        counts = tmg.sample_counts(B, 10000, "proj-set", seed=4, device=True)
+        a = tmg.point_estimate_batch(counts, cptp=False)
+        with nt.option("NO_TMA_GEMM", 1):
+            b = tmg.point_estimate_batch(counts, cptp=False)
+        assert np.array_equal(a, b), n
