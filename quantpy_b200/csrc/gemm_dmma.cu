@@ -163,10 +163,27 @@ __device__ __forceinline__ int4 ldg_counts4(const int32_t* p, bool ok) {
     return v;
 }
 
-template <bool ONE_GROUP>
+struct a4 {
+    double v[4];
+};
+__device__ __forceinline__ a4 ldg_f64x4(const double* p, bool ok) {
+    a4 r = {{0.0, 0.0, 0.0, 0.0}};
+    if (ok) {
+        const double2 lo = __ldg(reinterpret_cast<const double2*>(p)), hi = __ldg(reinterpret_cast<const double2*>(p) + 1);
+        r.v[0] = lo.x; r.v[1] = lo.y; r.v[2] = hi.x; r.v[3] = hi.y;
+    }
+    return r;
+}
+
+// MODE 0: left operand = int32 counts, one normalisation per row (linear inversion);  1: counts, one normalisation
+// per group of G columns ('lifp');  2: left operand = float64 rows (`xf`), output scaled by `inv_tot[0]`-free
+// epilogue: C = clip(scale * X T) -- the batched POVM-probability contraction p = 2^n M r (state.py:109-110).
+template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 2)
-k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ counts,
-                   const double* __restrict__ inv_tot, const double* __restrict__ T, double* __restrict__ C) {
+k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ counts, const double* __restrict__ xf,
+                   const double* __restrict__ inv_tot, const double* __restrict__ T, double* __restrict__ C,
+                   double scale, int clip) {
+    constexpr bool ONE_GROUP = MODE == 0;
     extern __shared__ __align__(128) unsigned char gsm[];
     GemmStage* stages = reinterpret_cast<GemmStage*>(gsm);
     uint64_t* full = reinterpret_cast<uint64_t*>(gsm + sizeof(GemmStage) * STAGES);
@@ -223,12 +240,22 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
         const long g0 = min((long)m0 + r0, (long)M - 1), g1 = min((long)m0 + r0 + 8, (long)M - 1);
         const int32_t* row0 = counts + g0 * Ktot + c4;
         const int32_t* row1 = counts + g1 * Ktot + c4;
+        const double* xrow0 = xf + g0 * Ktot + c4;
+        const double* xrow1 = xf + g1 * Ktot + c4;
         double inv0 = 0.0, inv1 = 0.0;
         if (ONE_GROUP) {
             inv0 = inv_tot[g0];
             inv1 = inv_tot[g1];
         }
-        int4 cur0 = ldg_counts4(row0, c4 + 3 < Ktot), cur1 = ldg_counts4(row1, c4 + 3 < Ktot);
+        int4 cur0 = make_int4(0, 0, 0, 0), cur1 = cur0;
+        a4 xc0 = {{0.0, 0.0, 0.0, 0.0}}, xc1 = xc0;
+        if (MODE == 2) {
+            xc0 = ldg_f64x4(xrow0, c4 + 3 < Ktot);
+            xc1 = ldg_f64x4(xrow1, c4 + 3 < Ktot);
+        } else {
+            cur0 = ldg_counts4(row0, c4 + 3 < Ktot);
+            cur1 = ldg_counts4(row1, c4 + 3 < Ktot);
+        }
         for (int c = 0; c < chunks; ++c, ++it) {
             const int s = (int)(it % STAGES);
             mbar_wait(&full[s], (unsigned)((it / STAGES) & 1));
@@ -239,13 +266,22 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
                 if (blk < nblk) {
                     const int kb = blk * 16;                                // first k of this block
                     const bool more = kb + 16 + c4 + 3 < Ktot;
-                    const int4 nxt0 = ldg_counts4(row0 + kb + 16, more), nxt1 = ldg_counts4(row1 + kb + 16, more);
+                    int4 nxt0 = cur0, nxt1 = cur1;
+                    a4 xn0 = xc0, xn1 = xc1;
+                    if (MODE == 2) {
+                        xn0 = ldg_f64x4(xrow0 + kb + 16, more);
+                        xn1 = ldg_f64x4(xrow1 + kb + 16, more);
+                    } else {
+                        nxt0 = ldg_counts4(row0 + kb + 16, more);
+                        nxt1 = ldg_counts4(row1 + kb + 16, more);
+                    }
                     const bool okk = kb + c4 + 3 < Ktot;                    // this lane's four k of the block exist
                     const int cc0[4] = {cur0.x, cur0.y, cur0.z, cur0.w}, cc1[4] = {cur1.x, cur1.y, cur1.z, cur1.w};
 #pragma unroll
                     for (int st = 0; st < 4; ++st) {
-                        double a0 = (double)cc0[st], a1 = (double)cc1[st];
-                        if (ONE_GROUP) {
+                        double a0 = MODE == 2 ? xc0.v[st] : (double)cc0[st], a1 = MODE == 2 ? xc1.v[st] : (double)cc1[st];
+                        if (MODE == 2) {
+                        } else if (ONE_GROUP) {
                             a0 *= inv0;
                             a1 *= inv1;
                         } else {
@@ -265,6 +301,8 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
                     }
                     cur0 = nxt0;
                     cur1 = nxt1;
+                    xc0 = xn0;
+                    xc1 = xn1;
                 }
             }
             __syncwarp();
@@ -276,11 +314,20 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
             for (int j = 0; j < 4; ++j) {
                 const int m = m0 + wm * 16 + i * 8 + (lane >> 2);
                 const int n = n0 + wn * 32 + j * 8 + 2 * (lane & 3);
+                double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                if (MODE == 2) {
+                    v0 *= scale;
+                    v1 *= scale;
+                    if (clip) {
+                        v0 = fmin(fmax(v0, 0.0), 1.0);
+                        v1 = fmin(fmax(v1, 0.0), 1.0);
+                    }
+                }
                 if (m < M) {
                     if (n + 1 < N) {
-                        *reinterpret_cast<double2*>(C + (long)m * N + n) = make_double2(acc[i][j][0], acc[i][j][1]);
+                        *reinterpret_cast<double2*>(C + (long)m * N + n) = make_double2(v0, v1);
                     } else if (n < N) {
-                        C[(long)m * N + n] = acc[i][j][0];
+                        C[(long)m * N + n] = v0;
                     }
                 }
             }
@@ -309,9 +356,45 @@ int launch_gemm_counts(int M, int N, int Ktot, int G, const int32_t* counts, con
     const long tiles = (long)((N + GN - 1) / GN) * ((M + GM - 1) / GM);
     long blocks = (long)num_sms() * 2;
     if (blocks > tiles) blocks = tiles;
-    auto kern = ng == 1 ? k_gemm_counts_dmma<true> : k_gemm_counts_dmma<false>;
+    auto kern = ng == 1 ? k_gemm_counts_dmma<0> : k_gemm_counts_dmma<1>;
     QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    kern<<<(int)blocks, kGemmThreads, kGemmSmem, st>>>(M, N, Ktot, G, counts, inv_tot, T, C);
+    kern<<<(int)blocks, kGemmThreads, kGemmSmem, st>>>(M, N, Ktot, G, counts, nullptr, inv_tot, T, C, 1.0, 0);
+    QPB_LAUNCHED("k_gemm_counts_dmma");
+    return QPB_OK;
+}
+
+// Table transpose for the probability contraction: Mt [D][K] = M [K][D]^T (once per call; the table is at most 2.65 MB)
+__global__ void k_transpose_f64(int rows, int cols, const double* __restrict__ in, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = in[(long)r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(long)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+// P [B][K] = clip(scale * X [B][D] * M [K][D]^T) on the FP64 tensor cores: the batched POVM-probability
+// contraction (state.py:109-110).  QPB_ERR_UNSUPPORTED when the shape does not fit the pipelined kernel.
+int launch_probs_gemm(int K, int D, int B, const double* Mtab, const double* X, double scale, int clip, double* P,
+                      cudaStream_t st) {
+    if (B < 64 || (D % 4) != 0 || (K % 2) != 0 || ((uintptr_t)X % 16) != 0 || option(QPB_OPT_NO_TMA_GEMM) ||
+        option(QPB_OPT_NO_DMMA_GEMM))
+        return QPB_ERR_UNSUPPORTED;
+    double* Mt = static_cast<double*>(scratch(st, 9, sizeof(double) * (size_t)K * D));
+    if (!Mt) return QPB_ERR_NOMEM;
+    k_transpose_f64<<<dim3((D + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(K, D, Mtab, Mt);
+    QPB_LAUNCHED("k_transpose_f64");
+    const long tiles = (long)((K + GN - 1) / GN) * ((B + GM - 1) / GM);
+    long blocks = (long)num_sms() * 2;
+    if (blocks > tiles) blocks = tiles;
+    auto kern = k_gemm_counts_dmma<2>;
+    QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    kern<<<(int)blocks, kGemmThreads, kGemmSmem, st>>>(B, K, D, D, nullptr, X, nullptr, Mt, P, scale, clip);
     QPB_LAUNCHED("k_gemm_counts_dmma");
     return QPB_OK;
 }

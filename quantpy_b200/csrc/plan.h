@@ -47,6 +47,9 @@ int mle_variant(const qpb_state_plan* plan);
 // C [M][N] = (counts [M][Ktot] normalised per group of G columns) * T [Ktot][N] on DMMA (gemm_dmma.cu)
 int launch_gemm_counts(int M, int N, int Ktot, int G, const int32_t* counts, const double* T, double* C,
                        cudaStream_t st);
+// P [B][K] = clip(scale * X [B][D] M [K][D]^T) on DMMA (gemm_dmma.cu); QPB_ERR_UNSUPPORTED for shapes it does not take
+int launch_probs_gemm(int K, int D, int B, const double* Mtab, const double* X, double scale, int clip, double* P,
+                      cudaStream_t st);
 int axis_plan_setup(qpb_state_plan* plan, const double* A_host);
 int launch_mle_axis(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                     double tol, double* rho, int32_t* iters, cudaStream_t st);

@@ -639,6 +639,10 @@ int qpb_povm_probs(int K, int D, int B, const double* M, const double* r, double
     QPB_REQUIRE(K > 0 && D > 0 && B >= 0, "bad shape K=%d D=%d B=%d", K, D, B);
     if (B == 0) return QPB_OK;
     QPB_REQUIRE(M && r && p, "NULL buffer");
+    {   // thousands of states: a genuine dense contraction -> FP64 tensor cores
+        const int rc = launch_probs_gemm(K, D, B, M, r, scale, clip, p, (cudaStream_t)stream);
+        if (rc != QPB_ERR_UNSUPPORTED) return rc;
+    }
     const size_t smem = sizeof(double) * PROBS_BT * (size_t)D;
     QPB_REQUIRE(smem <= 48 * 1024, "D=%d too large", D);
     const int grid = (B + PROBS_BT - 1) / PROBS_BT;
