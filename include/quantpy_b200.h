@@ -63,11 +63,23 @@ enum {
     QPB_OPT_MLE_W_WARPS = 15,    /* pauli2 MLE tuning: warp-per-sample workers per CTA from the start (0 = default, -1 = none) */
     QPB_OPT_MLE_PARK_PLATEAU = 16, /* pauli2 MLE tuning: first iteration count at which a non-decreasing step norm hands a sample over (0 = default, -1 = never) */
     QPB_OPT_NO_TMA_GEMM = 17,      /* counts GEMM: plain tiled DMMA kernel instead of the TMA/mbarrier pipeline */
-    QPB_OPT_COUNT_ = 18
+    QPB_OPT_MLE_TAIL_POLL = 18,    /* pauli2 MLE tuning: once the queue is empty, thread-per-sample warps look at the hand-over list every this many iterations (0 = default, -1 = never) */
+    QPB_OPT_MLE_TAIL_AGE = 19,     /* pauli2 MLE tuning: ... and give waiting workers their oldest sample if it is at least this old (0 = default) */
+    QPB_OPT_MLE_ADOPT = 20,        /* pauli2 MLE tuning: ... or adopt waiting entries into free lanes when at least this many wait (0 = default, -1 = never) */
+    QPB_OPT_MLE_MERGE = 21,        /* pauli2 MLE tuning: drained thread-per-sample warps of a CTA pack their samples into fewer warps when the others have at least live + this - 1 free lanes (0 = default, -1 = never) */
+    QPB_OPT_NO_MLE_ORDER = 22,     /* fused bootstrap: the pauli2 MLE starts the samples in index order instead of likely-long-runners first */
+    QPB_OPT_MLE_PARK_AGE_LO = 23,  /* pauli2 MLE tuning, with a start order: hand-over age of the first queue position (0 = default, -1 = same as MLE_PARK_AGE) */
+    QPB_OPT_MLE_PARK_AGE_PCT = 24, /* ... rising linearly to MLE_PARK_AGE over this percentage of the queue (0 = default) */
+    QPB_OPT_MLE_PARK_AGE_END = 25, /* ... and falling again for the samples started after the first wave of lanes, down to this age (0 = default: no fall) */
+    QPB_OPT_MLE_PARK_AGE_PCT2 = 26,/* ... over this percentage of the remaining queue (0 = default) */
+    QPB_OPT_COUNT_ = 27
 };
 QPB_API int qpb_set_option(int which, int value);
 QPB_API int qpb_get_option(int which);
 QPB_API int64_t qpb_launch_count(void);
+/* Profiling only: per-warp time stamps and work counters of the next k_mle_rrr_pauli2 launches are written to this
+ * device buffer (16 int64 words per warp; tools/pauli2_trace.py decodes them).  NULL switches it off (the default). */
+QPB_API int qpb_debug_set_trace(void* device_buffer, size_t bytes);
 QPB_API void qpb_reset_launch_count(void);
 
 /* Roofline probe (bench.py only): runs a pure FP64 FMA kernel on every SM; *flops_out_host receives the

@@ -32,6 +32,7 @@ SIGNATURES = {
     "qpb_abi_version": (_int, []),
     "qpb_last_error": (ctypes.c_char_p, []),
     "qpb_launch_count": (ctypes.c_int64, []),
+    "qpb_debug_set_trace": (_int, [_vp, ctypes.c_size_t]),
     "qpb_reset_launch_count": (None, []),
     "qpb_set_option": (_int, [_int, _int]),
     "qpb_get_option": (_int, [_int]),
@@ -68,7 +69,9 @@ SIGNATURES = {
 OPTIONS = {"NO_TAIL_MERGE": 0, "NO_HS_FUSION": 1, "NO_PAULI_KERNEL": 2, "NO_CONST_KERNEL": 3, "NO_AXIS_KERNEL": 4,
            "NO_DMMA_GEMM": 5, "NO_ROW_JACOBI": 6, "NO_PACKED_JACOBI": 7, "NO_LIN_SMALL": 8, "SAMPLER": 9,
            "MLE_BLOCKS_PER_SM": 10, "MLE_LANES": 11, "NO_TILED_MLE": 12, "MLE_PARK_AGE": 13, "MLE_PARK_LIVE": 14,
-           "MLE_W_WARPS": 15, "MLE_PARK_PLATEAU": 16, "NO_TMA_GEMM": 17}
+           "MLE_W_WARPS": 15, "MLE_PARK_PLATEAU": 16, "NO_TMA_GEMM": 17, "MLE_TAIL_POLL": 18, "MLE_TAIL_AGE": 19,
+           "MLE_ADOPT": 20, "MLE_MERGE": 21, "NO_MLE_ORDER": 22,
+           "MLE_PARK_AGE_LO": 23, "MLE_PARK_AGE_PCT": 24, "MLE_PARK_AGE_END": 25, "MLE_PARK_AGE_PCT2": 26}
 SAMPLERS = {"auto": 0, "alias": 1, "binomial": 2}
 
 

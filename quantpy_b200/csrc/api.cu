@@ -91,20 +91,29 @@ static const char* const kOptionEnv[QPB_OPT_COUNT_] = {
     "QPB_NO_TAIL_MERGE", "QPB_NO_HS_FUSION", "QPB_NO_PAULI_KERNEL", "QPB_NO_CONST_KERNEL", "QPB_NO_AXIS_KERNEL",
     "QPB_NO_DMMA_GEMM",  "QPB_NO_ROW_JACOBI", "QPB_NO_PACKED_JACOBI", "QPB_NO_LIN_SMALL",  "QPB_SAMPLER",
     "QPB_MLE_BLOCKS_PER_SM", "QPB_MLE_LANES", "QPB_NO_TILED_MLE",
-    "QPB_MLE_PARK_AGE", "QPB_MLE_PARK_LIVE", "QPB_MLE_W_WARPS", "QPB_MLE_PARK_PLATEAU", "QPB_NO_TMA_GEMM"};
+    "QPB_MLE_PARK_AGE", "QPB_MLE_PARK_LIVE", "QPB_MLE_W_WARPS", "QPB_MLE_PARK_PLATEAU", "QPB_NO_TMA_GEMM",
+    "QPB_MLE_TAIL_POLL", "QPB_MLE_TAIL_AGE", "QPB_MLE_ADOPT", "QPB_MLE_MERGE", "QPB_NO_MLE_ORDER",
+    "QPB_MLE_PARK_AGE_LO", "QPB_MLE_PARK_AGE_PCT", "QPB_MLE_PARK_AGE_END", "QPB_MLE_PARK_AGE_PCT2"};
 static const bool g_options_loaded = [] {
     for (int i = 0; i < QPB_OPT_COUNT_; ++i) {
         const char* e = kOptionEnv[i] ? getenv(kOptionEnv[i]) : nullptr;
         int v = 0;
         if (e && *e) {
             if (i == QPB_OPT_SAMPLER) v = !strcmp(e, "alias") ? 1 : (!strcmp(e, "binomial") ? 2 : 0);
-            else if (i >= QPB_OPT_MLE_BLOCKS_PER_SM && i != QPB_OPT_NO_TILED_MLE && i != QPB_OPT_NO_TMA_GEMM) v = atoi(e);
+            else if (i >= QPB_OPT_MLE_BLOCKS_PER_SM && i != QPB_OPT_NO_TILED_MLE && i != QPB_OPT_NO_TMA_GEMM &&
+                     i != QPB_OPT_NO_MLE_ORDER) v = atoi(e);
             else v = 1;
         }
         g_options[i].store(v);
     }
     return true;
 }();
+static std::atomic<long long*> g_trace_ptr{nullptr};
+static std::atomic<size_t> g_trace_bytes{0};
+long long* debug_trace_buffer(size_t bytes) {
+    long long* p = g_trace_ptr.load(std::memory_order_relaxed);
+    return (p && g_trace_bytes.load(std::memory_order_relaxed) >= bytes) ? p : nullptr;
+}
 int option(int which) { return (which >= 0 && which < QPB_OPT_COUNT_) ? g_options[which].load(std::memory_order_relaxed) : 0; }
 
 }  // namespace qpb
@@ -176,3 +185,9 @@ int64_t qpb_launch_count(void) { return qpb::g_launches.load(); }
 void qpb_reset_launch_count(void) { qpb::g_launches.store(0); }
 
 }  // extern "C"
+
+extern "C" int qpb_debug_set_trace(void* device_buffer, size_t bytes) {
+    qpb::g_trace_ptr.store(static_cast<long long*>(device_buffer));
+    qpb::g_trace_bytes.store(device_buffer ? bytes : 0);
+    return QPB_OK;
+}

@@ -64,18 +64,27 @@ int qpb_bootstrap_state(const qpb_state_plan* plan, int B, int P, int O, const d
         if (iters_out) QPB_CUDA(cudaMemsetAsync(iters_out, 0, sizeof(int32_t) * (size_t)B, st));
     } else {
         const double* start = nullptr;
+        const int* order = nullptr;
+        const bool pauli2 = max_iter > 0 && mle_variant(plan) == QPB_MLE_PAULI2;
         if (init == QPB_INIT_LIN) {
             // state.py:209: the start is point_estimate("lin") with its default physical=True
-            rc = qpb_lin_project(plan, B, counts_out, 1, buf0, stream);
+            rc = pauli2 ? launch_lin_project_small(plan, B, counts_out, 1, buf0, st, &order) : QPB_ERR_UNSUPPORTED;
+            if (rc == QPB_ERR_UNSUPPORTED) rc = qpb_lin_project(plan, B, counts_out, 1, buf0, stream);
             if (rc != QPB_OK) return rc;
             start = buf0;
         }
-        if (dist_kind == QPB_DIST_HS && max_iter > 0 && mle_variant(plan) == QPB_MLE_PAULI2) {
+        if (pauli2 && dist_kind != QPB_DIST_HS) {
+            rc = launch_mle_small(plan, B, counts_out, start, max_iter, tol, final_rho, iters_out, st, nullptr, nullptr,
+                                  nullptr, 1, order);
+            if (rc != QPB_OK) return rc;
+            return launch_distance(plan->d, B, final_rho, ref, dist_kind, dist, st);
+        }
+        if (dist_kind == QPB_DIST_HS && pauli2) {
             // two-qubit Pauli-axis POVMs: the MLE kernel writes the distances itself; the states are stored only if
             // the caller asked for them
             bool done = false;
             rc = launch_mle_small(plan, B, counts_out, start, max_iter, tol, final_rho, iters_out, st, ref, dist, &done,
-                                  rho_out ? 1 : 0);
+                                  rho_out ? 1 : 0, order);
             if (rc != QPB_OK) return rc;
             if (done) return QPB_OK;
             return launch_distance(plan->d, B, final_rho, ref, dist_kind, dist, st);

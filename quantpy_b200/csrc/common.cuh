@@ -28,6 +28,9 @@ extern std::atomic<int64_t> g_launches;
 // i.e. its contents are undefined.
 void* scratch(cudaStream_t st, int slot, size_t bytes, bool* fresh = nullptr);
 
+// Profiling: the buffer registered with qpb_debug_set_trace if it holds at least `bytes`, else nullptr.
+long long* debug_trace_buffer(size_t bytes);
+
 // Call right after a <<<>>> launch: counts it and surfaces launch-configuration errors.
 #define QPB_LAUNCHED(name)                                     \
     do {                                                       \

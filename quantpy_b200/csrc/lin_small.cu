@@ -74,16 +74,85 @@ __device__ __forceinline__ void jacobi_sweep<4>(RegMat<4>& A, RegMat<4>& V, doub
     jacobi_rotate<4, 1, 2>(A, V, tiny2);
 }
 
+// Scheduling class of a sample for the R.rho.R kernel that follows, from the smallest eigenvalue of the UNPROJECTED
+// linear estimate: negative -> the start state sits on the boundary and the iteration converges in a few dozen
+// steps (last class); small positive -> the long runners (first classes).  Log-spaced (4 classes per octave from
+// 2^-24), so no scale has to be known.  Only the ORDER in which samples are started depends on it, never a result.
+constexpr int kOrderClasses = 98;
+__device__ __forceinline__ int order_class(double mineig) {
+    if (!(mineig > 0.0)) return kOrderClasses - 1;
+    const int code = (int)((unsigned long long)__double_as_longlong(mineig) >> 50);  // exponent + 2 mantissa bits
+    const int lo = (1023 - 24) << 2;
+    const int cl = code - lo;
+    return cl < 0 ? 0 : (cl > kOrderClasses - 2 ? kOrderClasses - 2 : cl);
+}
+
+template <int N>
+__device__ __forceinline__ double lin_project_one(int K, long b, const double* __restrict__ tab,
+                                                  const int32_t* __restrict__ counts, int physical,
+                                                  double* __restrict__ rho);
+
 template <int N>
 __global__ void __launch_bounds__(kLinThreads)
 k_lin_project_small(int K, int B, const double* __restrict__ LhT, const int32_t* __restrict__ counts, int physical,
-                    double* __restrict__ rho) {
+                    double* __restrict__ rho, unsigned char* __restrict__ class_out, unsigned int* __restrict__ class_hist) {
     constexpr int d = 1 << N, D = d * d;
     extern __shared__ __align__(16) double tab[];  // [K][D]
+    __shared__ unsigned int hist_s[kOrderClasses];
     for (int e = threadIdx.x; e < K * D; e += kLinThreads) tab[e] = LhT[e];
+    if (class_out)
+        for (int e = threadIdx.x; e < kOrderClasses; e += kLinThreads) hist_s[e] = 0u;
     __syncthreads();
     const long b = (long)blockIdx.x * kLinThreads + threadIdx.x;
-    if (b >= B) return;
+    if (b < B) {
+        const double mineig = lin_project_one<N>(K, b, tab, counts, physical, rho);
+        if (class_out) {
+            const int cl = order_class(mineig);
+            class_out[b] = (unsigned char)cl;
+            atomicAdd(&hist_s[cl], 1u);
+        }
+    }
+    if (class_out) {  // uniform
+        __syncthreads();
+        for (int e = threadIdx.x; e < kOrderClasses; e += kLinThreads)
+            if (hist_s[e]) atomicAdd(&class_hist[e], hist_s[e]);
+    }
+}
+
+// order[pos] = sample index, classes ascending (long runners first); positions inside a class in arrival order
+__global__ void __launch_bounds__(256)
+k_order_scatter(int B, const unsigned char* __restrict__ cls, const unsigned int* __restrict__ hist,
+                unsigned int* __restrict__ fill, int* __restrict__ order) {
+    __shared__ unsigned int start_s[kOrderClasses], cnt_s[kOrderClasses], base_s[kOrderClasses];
+    const int t = threadIdx.x;
+    if (t < kOrderClasses) cnt_s[t] = 0u;
+    if (t == 0) {
+        unsigned int run = 0;
+        for (int e = 0; e < kOrderClasses; ++e) {
+            start_s[e] = run;
+            run += hist[e];
+        }
+    }
+    __syncthreads();
+    const long b = (long)blockIdx.x * 256 + t;
+    int cl = 0;
+    unsigned int rank = 0;
+    if (b < B) {
+        cl = cls[b];
+        rank = atomicAdd(&cnt_s[cl], 1u);
+    }
+    __syncthreads();
+    if (t < kOrderClasses && cnt_s[t]) base_s[t] = start_s[t] + atomicAdd(&fill[t], cnt_s[t]);
+    __syncthreads();
+    if (b < B) order[base_s[cl] + rank] = (int)b;
+}
+
+// returns the smallest eigenvalue of the unprojected estimate (0 when physical == 0: not computed)
+template <int N>
+__device__ __forceinline__ double lin_project_one(int K, long b, const double* __restrict__ tab,
+                                                  const int32_t* __restrict__ counts, int physical,
+                                                  double* __restrict__ rho) {
+    constexpr int d = 1 << N, D = d * d;
     const int32_t* c = counts + b * K;
     long long tot = 0;
     for (int k = 0; k < K; ++k) tot += c[k];
@@ -116,7 +185,7 @@ k_lin_project_small(int K, int B, const double* __restrict__ LhT, const int32_t*
         for (int a = 0; a < d; ++a)
 #pragma unroll
             for (int bb = 0; bb < d; ++bb) out[a * d + bb] = make_double2(A.re[a][bb], A.im[a][bb]);
-        return;
+        return 0.0;
     }
     RegMat<d> V;
 #pragma unroll
@@ -139,9 +208,10 @@ k_lin_project_small(int K, int B, const double* __restrict__ LhT, const int32_t*
         if (off <= 1e-30 * fro || fro == 0.0) break;  // relative off-diagonal norm 1e-15: eigenvalues are second order in it
         jacobi_sweep<d>(A, V, 1e-36 * fro);
     }
-    double lam[d], tr = 0.0;
+    double lam[d], tr = 0.0, mineig = A.re[0][0];
 #pragma unroll
     for (int j = 0; j < d; ++j) {
+        mineig = fmin(mineig, A.re[j][j]);
         lam[j] = fmax(A.re[j][j], kClipState);
         tr += lam[j];
     }
@@ -158,18 +228,37 @@ k_lin_project_small(int K, int B, const double* __restrict__ LhT, const int32_t*
             }
             out[a * d + bb] = make_double2(re * inv, im * inv);
         }
+    return mineig;
 }
 
 int launch_lin_project_small(const qpb_state_plan* plan, int B, const int32_t* counts, int physical, double* rho,
-                             cudaStream_t st) {
+                             cudaStream_t st, const int** order_out) {
+    if (order_out) *order_out = nullptr;
     if (plan->n > 2) return QPB_ERR_UNSUPPORTED;
     const size_t smem = sizeof(double) * (size_t)plan->K * plan->D;
     if (smem > 96 * 1024) return QPB_ERR_UNSUPPORTED;
     auto kern = plan->n == 1 ? k_lin_project_small<1> : k_lin_project_small<2>;
     if (smem > 48 * 1024) QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (B + kLinThreads - 1) / kLinThreads;
-    kern<<<grid, kLinThreads, smem, st>>>(plan->K, B, plan->LhT, counts, physical, rho);
+    // start order for the MLE kernel (only worth two more tiny launches when the batch spans several waves of lanes)
+    unsigned char* cls = nullptr;
+    unsigned int* hist = nullptr;
+    int* order = nullptr;
+    if (order_out && physical && B >= 4096 && !option(QPB_OPT_NO_MLE_ORDER)) {
+        unsigned char* base = static_cast<unsigned char*>(scratch(st, 10, 1024 + sizeof(int) * (size_t)B + (size_t)B));
+        if (!base) return QPB_ERR_NOMEM;
+        hist = reinterpret_cast<unsigned int*>(base);           // [kOrderClasses] histogram, then [kOrderClasses] fill
+        order = reinterpret_cast<int*>(base + 1024);
+        cls = base + 1024 + sizeof(int) * (size_t)B;
+        QPB_CUDA(cudaMemsetAsync(hist, 0, 1024, st));
+    }
+    kern<<<grid, kLinThreads, smem, st>>>(plan->K, B, plan->LhT, counts, physical, rho, cls, hist);
     QPB_LAUNCHED("k_lin_project_small");
+    if (cls) {
+        k_order_scatter<<<(B + 255) / 256, 256, 0, st>>>(B, cls, hist, hist + 128, order);
+        QPB_LAUNCHED("k_order_scatter");
+        *order_out = order;
+    }
     return QPB_OK;
 }
 

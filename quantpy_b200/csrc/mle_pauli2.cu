@@ -95,6 +95,7 @@ struct Pauli2Args {
     int B;
     const int32_t* counts;
     const double* rho0;
+    const int* order;     // queue position -> sample index (nullptr: identity)
     int max_iter;
     double tol;
     double* rho;
@@ -108,16 +109,32 @@ struct Pauli2Args {
     long long* park_b;    // [cap]
     int* park_it;         // [cap]
     unsigned int* park_ready;  // [cap]: == epoch once the entry is complete
+    unsigned int park_cap;     // entries of the list; a slot / ticket beyond it is void (the sample stays where it is)
     unsigned int epoch;
     int park_age;         // single-lane samples move to a W worker at this iteration count (INT_MAX: never)
+    int park_age_lo;      // ... with a start order: the sample at queue position q moves at park_age_lo + q * park_age_slope
+    int park_q2;          //     ... and from queue position park_q2 on (the samples that start after the first wave of
+    int park_age_end;     //     lanes) it falls again by park_age_slope2 per position, down to park_age_end: a late start
+    float park_age_slope2;//     leaves less time for the slow mapping
+    float park_age_slope; //     (capped at park_age): the first positions hold the likely long runners, whose chain
+                          //     of thread-per-sample iterations would otherwise end the launch
     int park_plateau;     // ... or from this iteration count on as soon as the step norm has not decreased over the
                           // last 32 iterations (the signature of the few-hundred-iteration plateaus; 0: off)
     int park_live;        // a drained warp with <= park_live live samples hands all of them over (0: never)
     int single_warps;     // warps [0, single_warps) start thread-per-sample, the others are W workers
+    int tail_poll;        // once the queue is empty a thread-per-sample warp looks at the hand-over list every tail_poll
+                          // iterations (power of two; 0: never): W workers waiting -> it hands over its oldest sample,
+                          // entries waiting -> its free lanes adopt them
+    int tail_age;         // ... samples younger than this stay where they are
+    int adopt;            // free lanes of a drained warp adopt waiting entries (0: W workers only)
+    int merge;            // drained thread-per-sample warps of a CTA pack their samples into fewer warps (0: off)
+    long long* trace_s;   // profiling: 4 words per sample (start, hand-over, pick-up, finish times), or null
+    long long* trace;     // profiling (qpb_debug_set_trace): 16 words per warp, see tools/pauli2_trace.py; normally null
     int direct;           // W workers take fresh samples from the queue (no single-lane warps)
 };
 
 constexpr int kPauliThreadsSingle = 256;  // thread-per-sample lanes per CTA (8 warps: 2 per scheduler)
+constexpr int kPoolWords = 54;             // a sample on the packing stack: 16 state + 36 frequencies + index + age
 
 // ------------------------------------------------------------------------------------------------
 // pieces of the dataflow graph shared by both mappings
@@ -126,6 +143,11 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ double flip(double x, unsigned neg) {  // neg ? -x : x, on the integer pipe
     return __hiloint2double(__double2hiint(x) ^ (int)(neg << 31), __double2loint(x));
 }
@@ -476,6 +498,9 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
     const double tol2 = a.tol * a.tol;
     const int K = pp.K;
     if (lane == 0) wb[ZERO] = 0.0;
+    long long* const tr_w = a.trace ? a.trace + 16 * ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : nullptr;
+    long long tr_samples = 0, tr_its = 0, tr_wait = 0;
+    if (tr_w && lane == 0) tr_w[8] = (long long)globaltimer_ns();
 
     for (;;) {
         // ---- next sample: a handed-over one (ticket order), or a fresh one in direct mode -----------------
@@ -485,14 +510,15 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
         if (lane == 0) {
             if (a.direct) {
                 const unsigned idx = atomicAdd(&a.ctrl[0], 1u);
-                if (idx < (unsigned)a.B) b = idx;
+                if (idx < (unsigned)a.B) b = a.order ? (long long)__ldg(a.order + idx) : (long long)idx;
             } else {
                 const unsigned ticket = atomicAdd(&a.ctrl[2], 1u);
                 unsigned ns = 64;
                 for (;;) {
-                    unsigned r;
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(a.park_ready + ticket) : "memory");
-                    if (r == a.epoch) {
+                    unsigned r = 0;
+                    if (ticket < a.park_cap)
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(a.park_ready + ticket) : "memory");
+                    if (ticket < a.park_cap && r == a.epoch) {
                         b = a.park_b[ticket];
                         it = a.park_it[ticket];
                         from_park = (int)ticket + 1;
@@ -507,8 +533,19 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
             }
         }
         b = __shfl_sync(full, b, 0);
-        if (b < 0) return;
+        if (b < 0) {
+            if (tr_w && lane == 0) {
+                tr_w[9] = (long long)globaltimer_ns();
+                tr_w[10] = tr_samples;
+                tr_w[11] = tr_its;
+                tr_w[12] = tr_wait;
+            }
+            return;
+        }
         it = __shfl_sync(full, it, 0);
+        const int tr_it0 = it;
+        const long long tr_t0 = tr_w ? (long long)globaltimer_ns() : 0;
+        if (a.trace_s && lane == 0) a.trace_s[4 * b + (from_park ? 2 : 0)] = tr_t0;
         from_park = __shfl_sync(full, from_park, 0);
         // ---- frequencies by slot, start state -----------------------------------------------------------
         __syncwarp();
@@ -658,6 +695,10 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
                 if (a.iters) a.iters[b] = it;
                 if (!a.direct) atomicAdd(&a.ctrl[3], 1u);
             }
+            if (a.trace_s && lane == 0) a.trace_s[4 * b + 3] = (long long)globaltimer_ns();
+            tr_samples += 1;
+            tr_its += it - tr_it0;
+            if (tr_w) tr_wait += (long long)globaltimer_ns() - tr_t0;  // busy time, in fact
         }
     }
 }
@@ -666,6 +707,22 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
+// frequencies of sample b into the lane's shared-memory column (slot-major, thread-minor)
+__device__ __forceinline__ void load_frequencies(const PauliParams& pp, const int32_t* __restrict__ c, int K,
+                                                 double* __restrict__ fcol) {
+    // all K count loads are issued together (independent, predicated), then normalised
+    int cc[36];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) cc[k] = (k < K) ? c[k] : 0;
+    long long tot = 0;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) tot += cc[k];
+    const FreqDiv freq((double)tot);
+#pragma unroll
+    for (int k = 0; k < 36; ++k)
+        if (k < K) fcol[pp.slot_of_col[k] * kPauliThreadsSingle] = freq((double)cc[k]);
+}
+
 template <bool UG>  // all used slots share one 1e-10/c: fold it into S_00 instead of 36 additions
 __global__ void __launch_bounds__(384, 1)
 k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__ Pauli2Args a) {
@@ -674,6 +731,18 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double* wbase = sm + (size_t)warp * wmode::SIZE;                     // W region of this warp
     double* fs = sm + (size_t)(blockDim.x >> 5) * wmode::SIZE;            // [36][256], thread-per-sample lanes only
+    // Packing of the tail (a.merge): once the queue is empty the live samples of a CTA's thread-per-sample warps thin
+    // out; a warp whose samples fit into the free lanes of the others pushes them (state, frequencies, index, age)
+    // onto a shared-memory stack, the others pop them into their free lanes, and the emptied warp becomes a W worker.
+    // live[w] (cx[0..7]): live lanes of warp w as last published, 32 before it saw the queue empty, -1 once it left;
+    // cx[8]: entries on the stack; cx[9]: lock (all stack / live[-1] transitions happen under it).
+    double* pool = fs + 36 * kPauliThreadsSingle;                          // [kPoolWords][32], entry-minor
+    volatile int* cx = reinterpret_cast<volatile int*>(pool + kPoolWords * 32);
+    if (a.merge) {
+        if (tid < 8) cx[tid] = tid < a.single_warps ? 32 : -1;
+        if (tid == 8 || tid == 9) cx[tid] = 0;
+        __syncthreads();
+    }
     if (warp >= a.single_warps) {
         wmode::worker<UG>(pp, a, wbase, lane);
         return;
@@ -682,11 +751,17 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
     for (int sl = 0; sl < 36; ++sl) fs[sl * kPauliThreadsSingle + tid] = 0.0;  // own column only: no barrier needed
 
     double h[D];
-    int it = 0;
+    int it = 0, my_age = a.park_age;
     long long b = -1;
     bool alive = true;  // false once the queue ran dry for this lane
     double del_ref = 0.0;   // step norm 32 iterations ago
     bool plateau = false;
+    unsigned tick = 0;
+    bool dissolved = false;  // this warp pushed its samples onto the packing stack
+    long long* const tr_s = a.trace ? a.trace + 16 * ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) : nullptr;
+    long long tr_wi = 0, tr_li = 0, tr_wi_tail = 0, tr_li_tail = 0, tr_parked = 0, tr_adopted = 0;
+    bool tr_seen_drain = false;
+    if (tr_s && lane == 0) tr_s[0] = (long long)globaltimer_ns();
     const double tol2 = a.tol * a.tol;
     const bool hand_over = a.single_warps < (int)(blockDim.x >> 5) || a.park_live > 0 || a.park_age < 0x7fffffff;
 
@@ -702,21 +777,17 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
             if (want) {
                 const long long nb = (long long)base + __popc(need & ((1u << lane) - 1u));
                 if (nb < a.B) {
-                    b = nb;
+                    b = a.order ? (long long)__ldg(a.order + nb) : nb;
+                    my_age = a.park_age;
+                    if (a.order) {
+                        my_age = min(a.park_age, a.park_age_lo + (int)((float)nb * a.park_age_slope));
+                        if (nb > a.park_q2)
+                            my_age = max(a.park_age_end, my_age - (int)((float)(nb - a.park_q2) * a.park_age_slope2));
+                    }
+                    if (a.trace_s) a.trace_s[4 * b] = (long long)globaltimer_ns();
                     it = 0;
                     plateau = false;
-                    // all K count loads are issued together (independent, predicated), then normalised
-                    const int32_t* c = a.counts + b * K;
-                    int cc[36];
-#pragma unroll
-                    for (int k = 0; k < 36; ++k) cc[k] = (k < K) ? c[k] : 0;
-                    long long tot = 0;
-#pragma unroll
-                    for (int k = 0; k < 36; ++k) tot += cc[k];
-                    const FreqDiv freq((double)tot);
-#pragma unroll
-                    for (int k = 0; k < 36; ++k)
-                        if (k < K) fs[pp.slot_of_col[k] * kPauliThreadsSingle + tid] = freq((double)cc[k]);
+                    load_frequencies(pp, a.counts + b * K, K, fs + tid);
                     if (a.rho0) {
                         const double2* r0 = reinterpret_cast<const double2*>(a.rho0) + b * D;
 #pragma unroll
@@ -736,37 +807,196 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
                 }
             }
         }
-        const unsigned active = __ballot_sync(0xffffffffu, b >= 0);
+        unsigned active = __ballot_sync(0xffffffffu, b >= 0);
         const bool drained = __any_sync(0xffffffffu, !alive);
-        if (active == 0) {
-            if (!drained) continue;  // cannot happen (a lane without work either refilled or saw the end)
+        if (active == 0 && !drained) continue;  // cannot happen (a lane without work either refilled or saw the end)
+        if (a.merge && drained) {
+            const unsigned full = 0xffffffffu;
+            auto lock = [&]() {
+                if (lane == 0)
+                    while (atomicCAS(const_cast<int*>(cx + 9), 0, 1) != 0) {}
+                __syncwarp();
+                __threadfence_block();
+            };
+            auto unlock = [&]() {
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) atomicExch(const_cast<int*>(cx + 9), 0);
+            };
+            auto pop = [&]() {  // under the lock: fill free lanes from the stack
+                const int top = cx[8];
+                const unsigned freem = ~active;
+                int n = __popc(freem);
+                if (n > top) n = top;
+                const int rank = __popc(freem & ((1u << lane) - 1u));
+                if (b < 0 && rank < n) {
+                    const double* src = pool + (top - 1 - rank);
+#pragma unroll
+                    for (int e = 0; e < D; ++e) h[e] = src[e * 32];
+#pragma unroll
+                    for (int sl = 0; sl < 36; ++sl) fs[sl * kPauliThreadsSingle + tid] = src[(16 + sl) * 32];
+                    b = __double_as_longlong(src[52 * 32]);
+                    it = (int)__double_as_longlong(src[53 * 32]);
+                    my_age = a.park_age;
+                    plateau = false;
+                    del_ref = 1e300;
+                }
+                active = __ballot_sync(full, b >= 0);
+                tr_adopted += n;
+                if (lane == 0) {
+                    cx[8] = top - n;
+                    cx[warp] = __popc(active);
+                }
+            };
+            if (active == 0) {  // leaving: nothing may stay on the stack without a warp to take it
+                lock();
+                if (!dissolved && cx[8] > 0) {
+                    pop();
+                    unlock();
+                    continue;
+                }
+                if (lane == 0) cx[warp] = -1;
+                unlock();
+                break;
+            }
+            const int live = __popc(active);
+            if (live < 32) {
+                if (lane == 0) cx[warp] = live;
+                if (cx[8] > 0) {
+                    lock();
+                    pop();
+                    unlock();
+                } else {
+                    const int lv = lane < 8 ? cx[lane] : -1;
+                    const int room = __reduce_add_sync(full, (lane != warp && lv >= 0) ? 32 - lv : 0);
+                    if (room >= live + a.merge - 1) {
+                        lock();
+                        const int top = cx[8];
+                        const int lv2 = lane < 8 ? cx[lane] : -1;
+                        const int room2 = __reduce_add_sync(full, (lane != warp && lv2 >= 0) ? 32 - lv2 : 0) - top;
+                        if (room2 >= live && top + live <= 32) {
+                            const int rank = __popc(active & ((1u << lane) - 1u));
+                            if (b >= 0) {
+                                double* dst = pool + (top + rank);
+#pragma unroll
+                                for (int e = 0; e < D; ++e) dst[e * 32] = h[e];
+#pragma unroll
+                                for (int sl = 0; sl < 36; ++sl) dst[(16 + sl) * 32] = fs[sl * kPauliThreadsSingle + tid];
+                                dst[52 * 32] = __longlong_as_double(b);
+                                dst[53 * 32] = __longlong_as_double((long long)it);
+                                b = -1;
+                            }
+                            if (lane == 0) {
+                                cx[8] = top + live;
+                                cx[warp] = -1;
+                            }
+                            dissolved = true;
+                            tr_parked += live;  // (trace: counted with the handed-over samples)
+                            active = 0;
+                        }
+                        unlock();
+                        if (dissolved) break;
+                    }
+                }
+            }
+        } else if (active == 0) {
             break;
+        }
+        if (tr_s && drained && !tr_seen_drain) {
+            tr_seen_drain = true;
+            if (lane == 0) {
+                tr_s[1] = (long long)globaltimer_ns();
+                tr_s[7] = __popc(active);
+            }
         }
         // ---- hand long-running samples to the W workers ---------------------------------------------------
         if (hand_over) {
-            bool park = b >= 0 && (it >= a.park_age || plateau);
+            const bool tail = drained && a.tail_poll > 0;
+            auto hand_over_entry = [&](unsigned slot) {
+                if (slot >= a.park_cap) return;  // list full: the sample stays in this lane
+                double2* dst = reinterpret_cast<double2*>(a.park_h + (size_t)slot * 16);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) __stcg(dst + e, make_double2(h[2 * e], h[2 * e + 1]));
+                a.park_b[slot] = b;
+                a.park_it[slot] = it;
+                if (a.trace_s) a.trace_s[4 * b + 1] = (long long)globaltimer_ns();
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.park_ready + slot), "r"(a.epoch) : "memory");
+                b = -1;
+            };
+            // bulk: by age (the W workers are a fixed share of the machine).  Tail: by demand, below.
+            bool park = b >= 0 && ((!tail && it >= my_age) || plateau);
             if (drained && __popc(active) <= a.park_live) park = b >= 0;
+            if (tail && ((++tick) & (a.tail_poll - 1)) == 0 && __popc(active) > a.park_live) {
+                // the queue is empty: look at the hand-over list.  waiting > 0: W workers without an entry -> give
+                // them this warp's oldest sample; waiting < 0: entries without a worker -> free lanes adopt them.
+                unsigned r = 0, t = 0;
+                if (lane == 0) {
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(a.ctrl + 1) : "memory");
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(t) : "l"(a.ctrl + 2) : "memory");
+                }
+                r = __shfl_sync(0xffffffffu, r, 0);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (r > a.park_cap) r = a.park_cap;
+                if (t > a.park_cap) t = a.park_cap;
+                const int waiting = (int)(t - r);
+                if (waiting > 0) {
+                    const int age = (b >= 0 && it >= a.tail_age) ? it : -1;
+                    const int oldest = __reduce_max_sync(0xffffffffu, age);
+                    if (oldest >= 0) {
+                        const int who = __ffs(__ballot_sync(0xffffffffu, age == oldest)) - 1;
+                        if (lane == who) park = true;
+                    }
+                } else if (a.adopt > 0 && -waiting >= a.adopt && ~active != 0u) {
+                    const unsigned freem = ~active;
+                    unsigned n = (unsigned)__popc(freem);
+                    if (n > (unsigned)(-waiting)) n = (unsigned)(-waiting);
+                    unsigned got = 0;
+                    if (lane == 0) got = atomicCAS(&a.ctrl[2], t, t + n);
+                    got = __shfl_sync(0xffffffffu, got, 0);
+                    if (got == t && b < 0 && (unsigned)__popc(freem & ((1u << lane) - 1u)) < n) {
+                        const unsigned ticket = t + (unsigned)__popc(freem & ((1u << lane) - 1u));
+                        unsigned ready;
+                        do {  // reserved before we looked, so its writer is on the way
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(ready) : "l"(a.park_ready + ticket) : "memory");
+                        } while (ready != a.epoch);
+                        b = a.park_b[ticket];
+                        it = a.park_it[ticket];
+                        my_age = a.park_age;
+                        plateau = false;
+                        del_ref = 1e300;
+                        const double2* src = reinterpret_cast<const double2*>(a.park_h + (size_t)ticket * 16);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const double2 z = __ldcg(src + e);
+                            h[2 * e] = z.x;
+                            h[2 * e + 1] = z.y;
+                        }
+                        load_frequencies(pp, a.counts + b * K, K, fs + tid);
+                    }
+                    tr_adopted += __popc(__ballot_sync(0xffffffffu, b >= 0)) - __popc(active);
+                    active = __ballot_sync(0xffffffffu, b >= 0);
+                }
+            }
             const unsigned pm = __ballot_sync(0xffffffffu, park);
+            tr_parked += __popc(pm);
             if (pm) {
                 unsigned slot0 = 0;
                 const int leader = __ffs(pm) - 1;
                 if (lane == leader) slot0 = atomicAdd(&a.ctrl[1], (unsigned)__popc(pm));
                 slot0 = __shfl_sync(0xffffffffu, slot0, leader);
-                if (park) {
-                    const unsigned slot = slot0 + __popc(pm & ((1u << lane) - 1u));
-                    double2* dst = reinterpret_cast<double2*>(a.park_h + (size_t)slot * 16);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) __stcg(dst + e, make_double2(h[2 * e], h[2 * e + 1]));
-                    a.park_b[slot] = b;
-                    a.park_it[slot] = it;
-                    __threadfence();
-                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.park_ready + slot), "r"(a.epoch) : "memory");
-                    b = -1;
-                }
-                if ((active & ~pm) == 0) continue;  // everything handed over: refill or leave
+                if (park) hand_over_entry(slot0 + __popc(pm & ((1u << lane) - 1u)));
+                active = __ballot_sync(0xffffffffu, b >= 0);
+                if (active == 0) continue;  // everything handed over: refill or leave
             }
         }
         // ---- one R.rho.R iteration (lanes without a sample are predicated off) ---------------
+        tr_wi += 1;
+        tr_li += __popc(active);
+        if (drained) {
+            tr_wi_tail += 1;
+            tr_li_tail += __popc(active);
+        }
         bool finished = false;
         if (b >= 0) {
             if (a.max_iter <= 0) {
@@ -798,12 +1028,22 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
             }
             if (a.hs_dist) a.hs_dist[b] = hs_distance_packed(h, a.hs_ref);
             if (a.iters) a.iters[b] = it;
+            if (a.trace_s) a.trace_s[4 * b + 3] = (long long)globaltimer_ns();
             b = -1;
         }
         if (hand_over) {
             const unsigned fin = __ballot_sync(0xffffffffu, finished);
             if (fin && lane == 0) atomicAdd(&a.ctrl[3], (unsigned)__popc(fin));
         }
+    }
+    if (tr_s && lane == 0) {
+        tr_s[2] = (long long)globaltimer_ns();
+        tr_s[3] = tr_wi;
+        tr_s[4] = tr_li;
+        tr_s[5] = tr_wi_tail;
+        tr_s[6] = tr_li_tail;
+        tr_s[13] = tr_parked;
+        tr_s[14] = tr_adopted;
     }
     // out of single-lane work: serve the hand-over list until every sample of the launch is finished
     if (hand_over) wmode::worker<UG>(pp, a, wbase, lane);
@@ -870,7 +1110,7 @@ bool plan_is_pauli2(const qpb_state_plan* plan) {
 
 int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                       double tol, double* rho, int32_t* iters, cudaStream_t st, const double* hs_ref, double* hs_dist,
-                      bool* hs_done, int hs_store_rho) {
+                      bool* hs_done, int hs_store_rho, const int* order) {
     static std::atomic<unsigned int> epoch_counter{1};
     PauliParams pp;
     if (!detect_pauli2(plan->A_host, plan->K, &pp)) return QPB_ERR_UNSUPPORTED;
@@ -880,6 +1120,7 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
     a.B = B;
     a.counts = counts;
     a.rho0 = rho0;
+    a.order = order;
     a.max_iter = max_iter;
     a.tol = tol;
     a.iters = iters;
@@ -905,8 +1146,13 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
         a.single_warps = 0;
         a.direct = 1;
         a.park_age = 0x7fffffff;
+        a.park_age_lo = 0x7fffffff;
+        a.park_age_slope = a.park_age_slope2 = 0.f;
+        a.park_q2 = 0x7fffffff;
+        a.park_age_end = 0x7fffffff;
         a.park_live = 0;
         a.park_plateau = 0;
+        a.tail_poll = a.tail_age = a.adopt = a.merge = 0;
         // warps per CTA: enough that every SM has work, at most 32 (profiling: MLE_BLOCKS_PER_SM overrides)
         int dw = option(QPB_OPT_MLE_BLOCKS_PER_SM) > 0 ? option(QPB_OPT_MLE_BLOCKS_PER_SM) : (int)(((long long)B + sms - 1) / sms);
         const int dw_max = option(QPB_OPT_MLE_W_WARPS) > 4 ? option(QPB_OPT_MLE_W_WARPS) : 16;  // profiling: 16 | 24 | 32
@@ -928,8 +1174,13 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
         a.single_warps = sw;
         if (no_merge) {
             a.park_age = 0x7fffffff;
+            a.park_age_lo = 0x7fffffff;
+            a.park_age_slope = a.park_age_slope2 = 0.f;
+            a.park_q2 = 0x7fffffff;
+            a.park_age_end = 0x7fffffff;
             a.park_live = 0;
             a.park_plateau = 0;
+            a.tail_poll = a.tail_age = a.adopt = a.merge = 0;
             w_warps = 0;
             a.single_warps = kPauliThreadsSingle / 32;
         } else {
@@ -940,8 +1191,33 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
             const long long lanes = (long long)sms * kPauliThreadsSingle;
             const int age = (long long)B * 2 <= lanes ? 200 : ((long long)B * 2 <= lanes * 3 ? 300 : 450);
             a.park_age = option(QPB_OPT_MLE_PARK_AGE) > 0 ? option(QPB_OPT_MLE_PARK_AGE) : age;
+            {
+                // measured on B200 (tools/pauli2_sweep_h.py): while most of the batch starts in the first wave of
+                // lanes a broad ramp from 250 pays; with several waves the W workers are too few for that
+                const bool few_waves = (long long)B * 2 <= lanes * 3;
+                const int lo = option(QPB_OPT_MLE_PARK_AGE_LO), pct = option(QPB_OPT_MLE_PARK_AGE_PCT);
+                a.park_age_lo = lo > 0 ? lo : (lo < 0 ? a.park_age : (few_waves ? 250 : 350));
+                if (a.park_age_lo > a.park_age) a.park_age_lo = a.park_age;
+                const double frac = (pct > 0 ? pct : (few_waves ? 50 : 10)) / 100.0;
+                a.park_age_slope = (float)((a.park_age - a.park_age_lo) / (frac * (double)B));
+                const int end = option(QPB_OPT_MLE_PARK_AGE_END), pct2 = option(QPB_OPT_MLE_PARK_AGE_PCT2);
+                a.park_q2 = (int)(lanes < B ? lanes : B);
+                a.park_age_end = end > 0 ? end : a.park_age;
+                if (a.park_age_end > a.park_age) a.park_age_end = a.park_age;
+                const double span = (pct2 > 0 ? pct2 : 50) / 100.0 * (double)(B - a.park_q2) + 1.0;
+                a.park_age_slope2 = (float)((a.park_age - a.park_age_end) / span);
+            }
             a.park_live = option(QPB_OPT_MLE_PARK_LIVE) > 0 ? option(QPB_OPT_MLE_PARK_LIVE) : ((long long)B * 4 <= lanes ? 16 : 5);
             if (a.single_warps < kPauliThreadsSingle / 32) w_warps = 12 - a.single_warps;
+            const int poll = option(QPB_OPT_MLE_TAIL_POLL);
+            a.tail_poll = poll < 0 ? 0 : (poll == 0 ? ((long long)B <= lanes ? 4 : 0) : poll);  // below one wave the W workers idle early
+            while (a.tail_poll & (a.tail_poll - 1)) a.tail_poll &= a.tail_poll - 1;  // power of two
+            a.tail_age = option(QPB_OPT_MLE_TAIL_AGE) > 0 ? option(QPB_OPT_MLE_TAIL_AGE) : 150;
+            const int ad = option(QPB_OPT_MLE_ADOPT);
+            a.adopt = ad <= 0 ? 0 : ad;      // measured: no gain, off by default
+            const int mg = option(QPB_OPT_MLE_MERGE);
+            a.merge = mg <= 0 ? 0 : mg;      // measured: fuller warps, but the launch ends later (the packed warps keep
+                                             // long runners on the slow mapping); off by default
         }
         threads = 32 * (a.single_warps + w_warps);
     }
@@ -950,7 +1226,9 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
     // slot 0: control words + ready flags (always at the same offset, so a stale word there is an older epoch or
     // zero, never data of another array); slots 7, 8: the hand-over entries
     const bool listed = !(a.direct || no_merge);
-    const size_t cap = listed ? (size_t)B + (size_t)blocks * 12 + 64 : 0;
+    // a sample can be handed over more than once (adoption by a thread-per-sample lane and back), hence 2 B
+    const size_t cap = listed ? 2 * (size_t)B + (size_t)blocks * 12 + 64 : 0;
+    a.park_cap = (unsigned)cap;
     bool fresh = false;
     unsigned char* base = static_cast<unsigned char*>(scratch(st, 0, 256 + sizeof(unsigned int) * cap, &fresh));
     if (!base) return QPB_ERR_NOMEM;
@@ -968,10 +1246,12 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
         if (fresh) QPB_CUDA(cudaMemsetAsync(base, 0, 256 + sizeof(unsigned int) * cap, st));  // no flag may hold a future epoch
     }
     QPB_CUDA(cudaMemsetAsync(a.ctrl, 0, 16, st));
+    a.trace = debug_trace_buffer(((size_t)blocks * (threads / 32) * 16 + 4 * (size_t)B) * sizeof(long long));
+    a.trace_s = a.trace ? a.trace + (size_t)blocks * (threads / 32) * 16 : nullptr;
     a.epoch = epoch_counter.fetch_add(1);
     if (a.epoch == 0) a.epoch = epoch_counter.fetch_add(1);
 
-    const size_t smem = sizeof(double) * ((size_t)(threads / 32) * wmode::SIZE + (a.direct ? 0 : 36 * kPauliThreadsSingle));
+    const size_t smem = sizeof(double) * ((size_t)(threads / 32) * wmode::SIZE + (a.direct ? 0 : 36 * kPauliThreadsSingle + kPoolWords * 32 + 8));
     auto pk = pp.uniform ? k_mle_rrr_pauli2<true> : k_mle_rrr_pauli2<false>;
     if (a.direct) {
         if (threads <= 512) pk = pp.uniform ? k_mle_rrr_pauli2_w<true, 512> : k_mle_rrr_pauli2_w<false, 512>;

@@ -392,7 +392,7 @@ static int launch_const(const qpb_state_plan* plan, int B, const int32_t* counts
 bool plan_is_pauli2(const qpb_state_plan* plan);
 int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                       double tol, double* rho, int32_t* iters, cudaStream_t st, const double* hs_ref, double* hs_dist,
-                      bool* hs_done, int hs_store_rho);
+                      bool* hs_done, int hs_store_rho, const int* order);
 
 // Which kernel qpb_mle_rrr will run for this plan (also exported through qpb_mle_variant for bench.py).
 int mle_variant(const qpb_state_plan* plan) {
@@ -408,14 +408,14 @@ int mle_variant(const qpb_state_plan* plan) {
 
 int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                      double tol, double* rho, int32_t* iters, cudaStream_t st, const double* hs_ref, double* hs_dist,
-                     bool* hs_done, int hs_store_rho) {
+                     bool* hs_done, int hs_store_rho, const int* order) {
     if (hs_done) *hs_done = false;
     if (plan->n > 2) return QPB_ERR_UNSUPPORTED;
     const size_t smem = sizeof(double) * ((size_t)plan->K * plan->D + (size_t)plan->K * kSmallThreads);
     if (smem > 200 * 1024) return QPB_ERR_UNSUPPORTED;
     if (plan->n == 2 && plan->A_host && !option(QPB_OPT_NO_PAULI_KERNEL)) {
         const int rc = launch_mle_pauli2(plan, B, counts, rho0, max_iter, tol, rho, iters, st, hs_ref, hs_dist, hs_done,
-                                         hs_store_rho);
+                                         hs_store_rho, order);
         if (rc != QPB_ERR_UNSUPPORTED) return rc;
     }
     unsigned int* queue = static_cast<unsigned int*>(scratch(st, 6, sizeof(unsigned int)));

@@ -27,8 +27,10 @@ namespace qpb {
 int launch_lin_project(const qpb_state_plan* plan, int B, const int32_t* counts, int physical, double* rho,
                        cudaStream_t st);
 // Register-resident variant for n <= 2 (lin_small.cu); QPB_ERR_UNSUPPORTED otherwise.
+// order_out (optional): receives a device array [B] with the order in which the R.rho.R kernel should start the
+// samples (likely long runners first, judged by the smallest eigenvalue of the unprojected estimate), or nullptr.
 int launch_lin_project_small(const qpb_state_plan* plan, int B, const int32_t* counts, int physical, double* rho,
-                             cudaStream_t st);
+                             cudaStream_t st, const int** order_out = nullptr);
 // Register-resident Jacobi + projection for d = 8, 16 from packed-Hermitian inputs H [B][d*d] (jacobi_rows.cu)
 int launch_project_rows(int d, int B, const double* h_in, double* rho, cudaStream_t st);
 int launch_mle_generic(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
@@ -41,7 +43,8 @@ int launch_distance(int d, int B, const double* rho, const double* ref, int kind
 // not written (rho must still be a valid buffer: kernels without the fusion use it).
 int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                      double tol, double* rho, int32_t* iters, cudaStream_t st, const double* hs_ref = nullptr,
-                     double* hs_dist = nullptr, bool* hs_done = nullptr, int hs_store_rho = 1);
+                     double* hs_dist = nullptr, bool* hs_done = nullptr, int hs_store_rho = 1,
+                     const int* order = nullptr);
 
 int mle_variant(const qpb_state_plan* plan);
 // C [M][N] = (counts [M][Ktot] normalised per group of G columns) * T [Ktot][N] on DMMA (gemm_dmma.cu)
