@@ -131,8 +131,10 @@ QPB_API int qpb_mle_rrr(const qpb_state_plan* plan, int B, const int32_t* counts
 /* Which R.rho.R kernel qpb_mle_rrr dispatches to for this plan (bench.py uses it to count flops):
  * GENERIC: warp per sample, any n<=4 | SMALL: thread per sample, table in shared memory |
  * CONST: thread per sample, table in constant bank, unrolled | PAULI2: two-qubit Pauli-axis POVM, no table |
- * AXIS: 3-4 qubit Pauli-axis POVM, CTA per sample, per-qubit axis maps + fast Pauli transform.  */
-enum { QPB_MLE_GENERIC = 0, QPB_MLE_SMALL = 1, QPB_MLE_CONST = 2, QPB_MLE_PAULI2 = 3, QPB_MLE_AXIS = 4 };
+ * AXIS: 3-4 qubit Pauli-axis POVM, CTA per sample, per-qubit axis maps + fast Pauli transform |
+ * TILED: unstructured POVM at 3-4 qubits, both contractions of an iteration as sample-tiled DMMA GEMMs with
+ *        TMA-staged tables (batches below 32 samples take GENERIC).  */
+enum { QPB_MLE_GENERIC = 0, QPB_MLE_SMALL = 1, QPB_MLE_CONST = 2, QPB_MLE_PAULI2 = 3, QPB_MLE_AXIS = 4, QPB_MLE_TILED = 5 };
 QPB_API int qpb_mle_variant(const qpb_state_plan* plan);
 
 /* k8: dist[b] = dst(rho[b], ref) with the reference's argument order dst(estimate, centre)

@@ -20,6 +20,7 @@ int qpb_mle_rrr(const qpb_state_plan* plan, int B, const int32_t* counts, const 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = launch_mle_small(plan, B, counts, rho0, max_iter, tol, rho, iters, st);
     if (rc == QPB_ERR_UNSUPPORTED) rc = launch_mle_axis(plan, B, counts, rho0, max_iter, tol, rho, iters, st);
+    if (rc == QPB_ERR_UNSUPPORTED && max_iter > 0) rc = launch_mle_tiled(plan, B, counts, rho0, max_iter, tol, rho, iters, st);
     if (rc == QPB_ERR_UNSUPPORTED) rc = launch_mle_generic(plan, B, counts, rho0, max_iter, tol, rho, iters, st);
     return rc;
 }

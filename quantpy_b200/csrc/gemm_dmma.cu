@@ -178,11 +178,15 @@ __device__ __forceinline__ a4 ldg_f64x4(const double* p, bool ok) {
 // MODE 0: left operand = int32 counts, one normalisation per row (linear inversion);  1: counts, one normalisation
 // per group of G columns ('lifp');  2: left operand = float64 rows (`xf`), output scaled by `inv_tot[0]`-free
 // epilogue: C = clip(scale * X T) -- the batched POVM-probability contraction p = 2^n M r (state.py:109-110).
+// MODE 3: like 2 with the rows of X taken through `rowmap` (the samples of a batched R.rho.R iteration that are still
+// running, mle_tiled.cu) and the likelihood-weight epilogue C[m][n] = fq[rowmap[m]][n] / (X T + 1e-10)
+// (gradient of state.py:228);  MODE 4: like 2 (rows of X direct), plain epilogue -- R = W A_r of the same iteration.
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 2)
 k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ counts, const double* __restrict__ xf,
                    const double* __restrict__ inv_tot, const double* __restrict__ T, double* __restrict__ C,
-                   double scale, int clip) {
+                   double scale, int clip, const int* __restrict__ rowmap, const double* __restrict__ fq) {
+    constexpr bool XF = MODE >= 2;  // float64 left operand
     constexpr bool ONE_GROUP = MODE == 0;
     extern __shared__ __align__(128) unsigned char gsm[];
     GemmStage* stages = reinterpret_cast<GemmStage*>(gsm);
@@ -240,8 +244,9 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
         const long g0 = min((long)m0 + r0, (long)M - 1), g1 = min((long)m0 + r0 + 8, (long)M - 1);
         const int32_t* row0 = counts + g0 * Ktot + c4;
         const int32_t* row1 = counts + g1 * Ktot + c4;
-        const double* xrow0 = xf + g0 * Ktot + c4;
-        const double* xrow1 = xf + g1 * Ktot + c4;
+        const long x0 = (MODE == 3) ? (long)rowmap[g0] : g0, x1 = (MODE == 3) ? (long)rowmap[g1] : g1;
+        const double* xrow0 = xf + x0 * Ktot + c4;
+        const double* xrow1 = xf + x1 * Ktot + c4;
         double inv0 = 0.0, inv1 = 0.0;
         if (ONE_GROUP) {
             inv0 = inv_tot[g0];
@@ -249,7 +254,7 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
         }
         int4 cur0 = make_int4(0, 0, 0, 0), cur1 = cur0;
         a4 xc0 = {{0.0, 0.0, 0.0, 0.0}}, xc1 = xc0;
-        if (MODE == 2) {
+        if (XF) {
             xc0 = ldg_f64x4(xrow0, c4 + 3 < Ktot);
             xc1 = ldg_f64x4(xrow1, c4 + 3 < Ktot);
         } else {
@@ -268,7 +273,7 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
                     const bool more = kb + 16 + c4 + 3 < Ktot;
                     int4 nxt0 = cur0, nxt1 = cur1;
                     a4 xn0 = xc0, xn1 = xc1;
-                    if (MODE == 2) {
+                    if (XF) {
                         xn0 = ldg_f64x4(xrow0 + kb + 16, more);
                         xn1 = ldg_f64x4(xrow1 + kb + 16, more);
                     } else {
@@ -279,8 +284,8 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
                     const int cc0[4] = {cur0.x, cur0.y, cur0.z, cur0.w}, cc1[4] = {cur1.x, cur1.y, cur1.z, cur1.w};
 #pragma unroll
                     for (int st = 0; st < 4; ++st) {
-                        double a0 = MODE == 2 ? xc0.v[st] : (double)cc0[st], a1 = MODE == 2 ? xc1.v[st] : (double)cc1[st];
-                        if (MODE == 2) {
+                        double a0 = XF ? xc0.v[st] : (double)cc0[st], a1 = XF ? xc1.v[st] : (double)cc1[st];
+                        if (XF) {
                         } else if (ONE_GROUP) {
                             a0 *= inv0;
                             a1 *= inv1;
@@ -323,6 +328,11 @@ k_gemm_counts_dmma(int M, int N, int Ktot, int G, const int32_t* __restrict__ co
                         v1 = fmin(fmax(v1, 0.0), 1.0);
                     }
                 }
+                if (MODE == 3 && m < M) {
+                    const double* fr = fq + (long)rowmap[m] * N + n;
+                    if (n < N) v0 = fr[0] / (v0 + kLogGuard);
+                    if (n + 1 < N) v1 = fr[1] / (v1 + kLogGuard);
+                }
                 if (m < M) {
                     if (n + 1 < N) {
                         *reinterpret_cast<double2*>(C + (long)m * N + n) = make_double2(v0, v1);
@@ -358,7 +368,7 @@ int launch_gemm_counts(int M, int N, int Ktot, int G, const int32_t* counts, con
     if (blocks > tiles) blocks = tiles;
     auto kern = ng == 1 ? k_gemm_counts_dmma<0> : k_gemm_counts_dmma<1>;
     QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    kern<<<(int)blocks, kGemmThreads, kGemmSmem, st>>>(M, N, Ktot, G, counts, nullptr, inv_tot, T, C, 1.0, 0);
+    kern<<<(int)blocks, kGemmThreads, kGemmSmem, st>>>(M, N, Ktot, G, counts, nullptr, inv_tot, T, C, 1.0, 0, nullptr, nullptr);
     QPB_LAUNCHED("k_gemm_counts_dmma");
     return QPB_OK;
 }
@@ -394,7 +404,26 @@ int launch_probs_gemm(int K, int D, int B, const double* Mtab, const double* X, 
     if (blocks > tiles) blocks = tiles;
     auto kern = k_gemm_counts_dmma<2>;
     QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
-    kern<<<(int)blocks, kGemmThreads, kGemmSmem, st>>>(B, K, D, D, nullptr, X, nullptr, Mt, P, scale, clip);
+    kern<<<(int)blocks, kGemmThreads, kGemmSmem, st>>>(B, K, D, D, nullptr, X, nullptr, Mt, P, scale, clip, nullptr, nullptr);
+    QPB_LAUNCHED("k_gemm_counts_dmma");
+    return QPB_OK;
+}
+
+// The two contractions of one batched R.rho.R iteration over the M samples still running (mle_tiled.cu):
+//   weights:  W [M][K] = fq[rowmap[m]][k] / (sum_i H2[rowmap[m]][i] ArT[i][k] + 1e-10)      (rowmap, fq given)
+//   operator: R [M][D] = sum_k W[m][k] Ar[k][i]                                             (rowmap == nullptr)
+// X rows and T rows must be 16-byte aligned, Kd % 4 == 0, N even (4^n and even K always are).
+int launch_gemm_f64(int M, int N, int Kd, const double* X, const int* rowmap, const double* fq, const double* T,
+                    double* C, cudaStream_t st) {
+    QPB_REQUIRE((Kd % 4) == 0 && (N % 2) == 0 && ((uintptr_t)X % 16) == 0 && ((uintptr_t)T % 16) == 0,
+                "bad f64 GEMM shape N=%d K=%d", N, Kd);
+    if (M <= 0) return QPB_OK;
+    const long tiles = (long)((N + GN - 1) / GN) * ((M + GM - 1) / GM);
+    long blocks = (long)num_sms() * 2;
+    if (blocks > tiles) blocks = tiles;
+    auto kern = rowmap ? k_gemm_counts_dmma<3> : k_gemm_counts_dmma<4>;
+    QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    kern<<<(int)blocks, kGemmThreads, kGemmSmem, st>>>(M, N, Kd, Kd, nullptr, X, nullptr, T, C, 1.0, 0, rowmap, fq);
     QPB_LAUNCHED("k_gemm_counts_dmma");
     return QPB_OK;
 }

@@ -396,7 +396,10 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
 
 // Which kernel qpb_mle_rrr will run for this plan (also exported through qpb_mle_variant for bench.py).
 int mle_variant(const qpb_state_plan* plan) {
-    if (plan->n > 2) return (plan->axis_ok && !option(QPB_OPT_NO_AXIS_KERNEL)) ? QPB_MLE_AXIS : QPB_MLE_GENERIC;
+    if (plan->n > 2) {
+        if (plan->axis_ok && !option(QPB_OPT_NO_AXIS_KERNEL)) return QPB_MLE_AXIS;
+        return mle_tiled_applicable(plan) ? QPB_MLE_TILED : QPB_MLE_GENERIC;  // (batches below 32 still take GENERIC)
+    }
     if (plan->n == 2 && plan->A_host && !option(QPB_OPT_NO_PAULI_KERNEL) && plan_is_pauli2(plan)) return QPB_MLE_PAULI2;
     if (plan->Ar_host && !option(QPB_OPT_NO_CONST_KERNEL)) {
         if ((plan->n == 2 && (plan->K == 36 || plan->K == 16)) || (plan->n == 1 && (plan->K == 6 || plan->K == 4)))

@@ -46,6 +46,12 @@ int launch_mle_small(const qpb_state_plan* plan, int B, const int32_t* counts, c
                      double* hs_dist = nullptr, bool* hs_done = nullptr, int hs_store_rho = 1,
                      const int* order = nullptr);
 
+// Batched general-POVM R.rho.R at n = 3, 4 on the DMMA GEMM (mle_tiled.cu); QPB_ERR_UNSUPPORTED for small batches
+// or when switched off, in which case the caller uses the warp-per-sample kernel.
+bool mle_tiled_applicable(const qpb_state_plan* plan);
+int launch_mle_tiled(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
+                     double tol, double* rho, int32_t* iters, cudaStream_t st);
+
 int mle_variant(const qpb_state_plan* plan);
 // C [M][N] = (counts [M][Ktot] normalised per group of G columns) * T [Ktot][N] on DMMA (gemm_dmma.cu)
 int launch_gemm_counts(int M, int N, int Ktot, int G, const int32_t* counts, const double* T, double* C,

@@ -342,6 +342,38 @@ def test_process_states_method_batched(qp, golden, n, method):
     assert itv.dist.shape == (300,) and np.all(np.diff(itv.dist) >= 0) and itv.dist[0] > 0
 
 
+def test_start_order_and_hand_over_policies_keep_every_bit(qp):
+    """The fused bootstrap starts the likely long runners first (order from the linear estimate's smallest eigenvalue)
+    and moves long-running samples between lane mappings; none of that may change a bit of any distance or
+    iteration count: every policy equals the plain thread-per-sample launch in index order."""
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    rho = haar(2, 3)
+    povm = qp.generate_measurement_matrix("proj", 2)
+    plan = engine.state_plan(povm, np.ones(1) * 10000)
+    probs = plan.probabilities(qp.Qobj(rho).bloch)[0].contiguous()
+    ref = nt.complex_to_device(rho)
+    for B in (5000, 60000):
+        bufs = plan.bootstrap_buffers(B)
+        with nt.option("NO_TAIL_MERGE", 1), nt.option("NO_MLE_ORDER", 1):
+            plan.bootstrap_into(bufs, probs, ref, 11, 0, method="mle", max_iter=1000, tol=1e-6)
+        want_d, want_it = bufs["dist"].clone(), bufs["iters"].clone()
+        settings = [{}, {"NO_MLE_ORDER": 1}, {"MLE_MERGE": 1}, {"MLE_TAIL_POLL": 4, "MLE_ADOPT": 8, "MLE_PARK_LIVE": 12},
+                    {"MLE_PARK_AGE": 150, "MLE_PARK_AGE_LO": 60, "MLE_PARK_AGE_END": 80},
+                    {"MLE_MERGE": 4, "MLE_TAIL_POLL": 2, "MLE_TAIL_AGE": 32, "MLE_ADOPT": 1}]
+        for opts in settings:
+            import contextlib
+            with contextlib.ExitStack() as stack:
+                for k, v in opts.items():
+                    stack.enter_context(nt.option(k, v))
+                bufs["dist"].zero_()
+                bufs["iters"].zero_()
+                plan.bootstrap_into(bufs, probs, ref, 11, 0, method="mle", max_iter=1000, tol=1e-6)
+            assert bool((bufs["dist"] == want_d).all()) and bool((bufs["iters"] == want_it).all()), (B, opts)
+        assert int(want_it.max()) > 300
+
+
 @pytest.mark.parametrize("n", [1, 2, 31, 1000, 4097, 12500, 16384, 16385, 100000])
 def test_sort_kernels_match_numpy(qp, n):
     """qpb_sort_f64: shared-memory bitonic network up to 16384 keys, device radix sort above; keys only, bit-exact."""

@@ -326,6 +326,40 @@ def test_mle_bench_setting_stragglers_match_oracle(qp):
     _check_off_by_one(tmg, counts[pick], got[pick], its[pick], wits)
 
 
+@pytest.mark.parametrize("n,B,max_iter", [(3, 331, 300), (4, 70, 12)])
+def test_tiled_general_povm_mle_matches_oracle(qp, n, B, max_iter):
+    """k_gemm_counts_dmma-based batched R.rho.R ('sic' POVM: no Pauli-axis structure) with per-sample stopping,
+    compaction of the running set every 8 iterations and a ragged batch: iteration counts equal the oracle's
+    (or one apart, checked at one-step distance), states 1e-10; the warp-per-sample kernel gives the same."""
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    rho = haar(n, 70 + n)
+    tmg = qp.StateTomograph(qp.Qobj(rho))
+    np.random.seed(n)
+    tmg.experiment(10000, "sic")
+    plan = engine.state_plan(tmg.povm_matrix, tmg.n_measurements)
+    assert nt.load_library().qpb_mle_variant(plan.handle) == 5
+    counts = tmg.sample_counts(B, 10000, "sic", seed=9)
+    tol = 1e-5 if n == 3 else 0.0
+    got, its = tmg.point_estimate_batch(counts, "mle", max_iter=max_iter, tol=tol, return_iters=True)
+    want, wits = ostate.mle_rrr(counts, tmg.povm_matrix, tmg.n_measurements, max_iter=max_iter, tol=tol,
+                                return_iters=True)
+    same = its == wits
+    assert same.mean() > 0.99
+    assert fro(got[same], want[same]).max() < 1e-10
+    _check_off_by_one(tmg, counts, got, its, wits)
+    if n == 3:
+        assert its.min() < its.max() and 1 < its.mean() < max_iter
+    with nt.option("NO_TILED_MLE", 1):
+        ref, rits = tmg.point_estimate_batch(counts, "mle", max_iter=max_iter, tol=tol, return_iters=True)
+    assert (rits == its).mean() > 0.99
+    assert fro(got[rits == its], ref[rits == its]).max() < 1e-11
+    mixed = tmg.point_estimate_batch(counts[:40], "mle", init="mixed", max_iter=3, tol=0.0)
+    assert fro(mixed, ostate.mle_rrr(counts[:40], tmg.povm_matrix, tmg.n_measurements, init="mixed", max_iter=3,
+                                     tol=0.0)).max() < 1e-10
+
+
 def test_mle_four_qubits_deep_iterations_match_oracle(qp):
     """k_mle_rrr_axis<4> at the depth the bench runs it: 200 iterations on 32 count tables, a quarter of them
     drawn from a rank-1 state (zero counts, probabilities at the 1e-10 guard) -- DMMA accumulation order and
@@ -349,7 +383,7 @@ def test_mle_four_qubits_deep_iterations_match_oracle(qp):
     (2, "proj", [], 3), (2, "proj", ["PAULI"], 2), (2, "proj", ["PAULI", "CONST"], 1),
     (2, "proj-set", [], 3), (2, "proj4", [], 3), (2, "sic", [], 2), (2, "sic", ["CONST"], 1),
     (1, "proj-set", [], 2), (1, "proj-set", ["CONST"], 1),
-    (3, "proj", [], 4), (3, "proj", ["AXIS"], 0), (3, "proj-set", [], 4), (3, "sic", [], 0), (4, "proj", [], 4),
+    (3, "proj", [], 4), (3, "proj", ["AXIS"], 5), (3, "proj", ["AXIS", "TILED_MLE"], 0), (3, "proj-set", [], 4), (3, "sic", [], 5), (3, "sic", ["TILED_MLE"], 0), (4, "proj", [], 4), (4, "sic", [], 5),
 ])
 def test_every_mle_kernel_variant_matches_oracle(qp, n, povm, disable, expect):
     """qpb_mle_rrr dispatches on the POVM's structure; every variant is the same update to 1e-10."""
@@ -360,7 +394,7 @@ def test_every_mle_kernel_variant_matches_oracle(qp, n, povm, disable, expect):
 
     with contextlib.ExitStack() as stack:
         for name in disable:
-            stack.enter_context(nt.option(f"NO_{name}_KERNEL", 1))
+            stack.enter_context(nt.option(f"NO_{name}" if name == "TILED_MLE" else f"NO_{name}_KERNEL", 1))
         _check_mle_variant(qp, n, povm, expect)
 
 
@@ -374,7 +408,7 @@ def _check_mle_variant(qp, n, povm, expect):
     tmg.experiment(10000, povm)
     plan = engine.state_plan(tmg.povm_matrix, tmg.n_measurements)
     assert nt.load_library().qpb_mle_variant(plan.handle) == expect
-    B = {1: 500, 2: 500, 3: 60, 4: 6}[n]
+    B = {1: 500, 2: 500, 3: 60, 4: 6 if expect != 5 else 40}[n]
     counts = tmg.sample_counts(B, 10000, povm, seed=17)
     tol, max_iter = (1e-5, 40) if n < 4 else (0.0, 4)
     got, its = tmg.point_estimate_batch(counts, "mle", max_iter=max_iter, tol=tol, return_iters=True)
