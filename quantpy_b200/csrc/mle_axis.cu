@@ -573,4 +573,94 @@ int launch_mle_axis(const qpb_state_plan* plan, int B, const int32_t* counts, co
     return QPB_ERR_UNSUPPORTED;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The per-sample half of the batched general-POVM iteration (mle_tiled.cu): rho' = R rho R / Tr from the packed R
+// rows the GEMM produced, with the same matrix helpers as the axis kernel (DMMA products at n = 4).  One CTA of
+// Axis<N>::GS threads per running sample; frozen (converged) samples are skipped until the row map drops them.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(Axis<N>::GS)
+k_rrr_update_mat(int M, const int* __restrict__ map, const double* __restrict__ R, double* __restrict__ H,
+                 double* __restrict__ H2, int* __restrict__ its, int* __restrict__ done, int max_iter, double tol) {
+    constexpr int d = Axis<N>::d, D = Axis<N>::D, MAT = Axis<N>::mat, GS = Axis<N>::GS;
+    extern __shared__ __align__(16) double smd[];
+    __shared__ double red[32];
+    const int lane = threadIdx.x;
+    const Mat<N> rho{smd}, Rm{smd + MAT}, P1{smd + 2 * MAT}, T{smd + 3 * MAT};
+    for (long a = blockIdx.x; a < M; a += gridDim.x) {
+        const int b = map[a];
+        if (done[b]) continue;  // uniform over the CTA
+        __syncthreads();
+        const double* Rp = R + a * D;
+        double* Hp = H + (long)b * D;
+        double* H2p = H2 + (long)b * D;
+        for (int e = lane; e < D; e += GS) {  // packed Hermitian -> full complex matrices
+            const int r = e / d, c = e % d;
+            if (r > c) continue;
+            const double rr = Rp[r * d + c], ri = (r == c) ? 0.0 : Rp[c * d + r];
+            const double hr = Hp[r * d + c], hi = (r == c) ? 0.0 : Hp[c * d + r];
+            Rm.set(r, c, make_double2(rr, ri));
+            rho.set(r, c, make_double2(hr, hi));
+            if (r != c) {
+                Rm.set(c, r, make_double2(rr, -ri));
+                rho.set(c, r, make_double2(hr, -hi));
+            }
+        }
+        gsync<GS>();
+        cmatmul<N, GS>(P1, Rm, rho, lane);  // R rho
+        cmatmul<N, GS>(T, P1, Rm, lane);    // R rho R
+        double tr = 0.0;
+        for (int x = lane; x < d; x += GS) tr += T.get(x, x).x;
+        tr = gsum<GS>(tr, red, lane);
+        const double inv = 1.0 / tr;
+        double del = 0.0;
+        for (int e = lane; e < D; e += GS) {
+            const int r = e / d, c = e % d;
+            if (r > c) continue;
+            const double2 old = rho.get(r, c);
+            if (r == c) {
+                const double v = T.get(r, r).x * inv;
+                const double dr = v - old.x;
+                del += dr * dr;
+                Hp[r * d + r] = v;
+                H2p[r * d + r] = v;
+            } else {
+                const double2 z = T.get(r, c), zt = T.get(c, r);
+                const double vr = 0.5 * (z.x + zt.x) * inv, vi = 0.5 * (z.y - zt.y) * inv;
+                const double dr = vr - old.x, di = vi - old.y;
+                del += 2.0 * (dr * dr + di * di);
+                Hp[r * d + c] = vr;
+                Hp[c * d + r] = vi;
+                H2p[r * d + c] = 2.0 * vr;
+                H2p[c * d + r] = 2.0 * vi;
+            }
+        }
+        del = sqrt(gsum<GS>(del, red, lane));
+        if (lane == 0) {
+            const int it = its[b] + 1;
+            its[b] = it;
+            if (del < tol || it >= max_iter) done[b] = 1;
+        }
+    }
+}
+
+template <int N>
+static int launch_update_mat(int M, const int* map, const double* R, double* H, double* H2, int* its, int* done,
+                             int max_iter, double tol, cudaStream_t st) {
+    const size_t smem = sizeof(double) * 4 * Axis<N>::mat;
+    long blocks = (long)num_sms() * (N == 4 ? 8 : 16);
+    if (blocks > M) blocks = M;
+    k_rrr_update_mat<N><<<(int)blocks, Axis<N>::GS, smem, st>>>(M, map, R, H, H2, its, done, max_iter, tol);
+    QPB_LAUNCHED("k_rrr_update_mat");
+    return QPB_OK;
+}
+
+int launch_rrr_update_mat(int n, int M, const int* map, const double* R, double* H, double* H2, int* its, int* done,
+                          int max_iter, double tol, cudaStream_t st) {
+    if (M <= 0) return QPB_OK;
+    if (n == 3) return launch_update_mat<3>(M, map, R, H, H2, its, done, max_iter, tol, st);
+    if (n == 4) return launch_update_mat<4>(M, map, R, H, H2, its, done, max_iter, tol, st);
+    return QPB_ERR_UNSUPPORTED;
+}
+
 }  // namespace qpb

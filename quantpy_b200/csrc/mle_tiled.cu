@@ -3,7 +3,7 @@
 //
 //   p_k = Tr(E_k rho) = sum_i ArT[i][k] h2[i]        W [M][K] = f / (H2 [M][D] * ArT [D][K] + 1e-10)     (GEMM 1 + epilogue)
 //   R   = sum_k w_k E_k                                R [M][D] = W [M][K] * Ar [K][D]                     (GEMM 2)
-//   rho' = R rho R / Tr(R rho R), step norm, stop      one warp per sample                                 (k_tiled_update)
+//   rho' = R rho R / Tr(R rho R), step norm, stop      one CTA per sample, DMMA products at n = 4          (k_rrr_update_mat)
 //
 // M = samples still running.  Both GEMMs are k_gemm_counts_dmma (gemm_dmma.cu): persistent 64 x 64 tiles, table
 // operand staged by TMA bulk copies into an mbarrier ring, DMMA m8n8k4.  The warp-per-sample kernel this replaces
@@ -20,6 +20,9 @@ namespace qpb {
 
 int launch_gemm_f64(int M, int N, int Kd, const double* X, const int* rowmap, const double* fq, const double* T,
                     double* C, cudaStream_t st);
+// rho' = R rho R / Tr, step norm and stopping rule for the running samples (mle_axis.cu: one CTA per sample, DMMA products)
+int launch_rrr_update_mat(int n, int M, const int* map, const double* R, double* H, double* H2, int* its, int* done,
+                          int max_iter, double tol, cudaStream_t st);
 
 constexpr int kChunk = 8;  // iterations between compactions of the running set
 
@@ -56,100 +59,30 @@ __global__ void k_tiled_init(int d, int K, int B, const int32_t* __restrict__ co
     }
 }
 
-// rho' = R rho R / Tr, step norm, convergence; one warp per running sample.  shared per warp: Rh | h | hn | S (cplx)
-__global__ void k_tiled_update(int d, int M, const int* __restrict__ map, const double* __restrict__ R,
-                               double* __restrict__ H, double* __restrict__ H2, int* __restrict__ its,
-                               int* __restrict__ done, int max_iter, double tol) {
-    extern __shared__ __align__(16) double usm[];
-    const int dd = d * d;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    double* Rh = usm + (size_t)warp * 5 * dd;
-    double* h = Rh + dd;
-    double* hn = h + dd;
-    cplx* S = reinterpret_cast<cplx*>(hn + dd);
-    for (long a = (long)blockIdx.x * nw + warp; a < M; a += (long)gridDim.x * nw) {
-        const int b = map[a];
-        if (done[b]) continue;  // frozen until the next compaction drops it from the map
-        for (int e = lane; e < dd; e += 32) {
-            Rh[e] = R[a * dd + e];
-            h[e] = H[(long)b * dd + e];
-        }
-        __syncwarp();
-        for (int e = lane; e < dd; e += 32) {  // S = R rho
-            const int r = e / d, c = e % d;
-            double re = 0.0, im = 0.0;
-            for (int k = 0; k < d; ++k) {
-                const cplx x = herm_get(Rh, d, r, k), y = herm_get(h, d, k, c);
-                re += x.re * y.re - x.im * y.im;
-                im += x.re * y.im + x.im * y.re;
-            }
-            S[e].re = re;
-            S[e].im = im;
-        }
-        __syncwarp();
-        double tr = 0.0;
-        for (int e = lane; e < dd; e += 32) {  // rho' = S R, upper triangle (Hermitian), packed
-            const int r = e / d, c = e % d;
-            if (r > c) continue;
-            double re = 0.0, im = 0.0;
-            for (int k = 0; k < d; ++k) {
-                const cplx x = S[r * d + k], y = herm_get(Rh, d, k, c);
-                re += x.re * y.re - x.im * y.im;
-                im += x.re * y.im + x.im * y.re;
-            }
-            hn[r * d + c] = re;
-            if (r != c) hn[c * d + r] = im;
-            else tr += re;
-        }
-        tr = warp_sum(tr);
-        __syncwarp();
-        const double inv = 1.0 / tr;
-        double del = 0.0;
-        for (int e = lane; e < dd; e += 32) {
-            const bool diag = (e / d == e % d);
-            const double v = hn[e] * inv;
-            const double df = v - h[e];
-            del += (diag ? 1.0 : 2.0) * df * df;
-            H[(long)b * dd + e] = v;
-            H2[(long)b * dd + e] = diag ? v : 2.0 * v;
-        }
-        del = sqrt(warp_sum(del));
-        if (lane == 0) {
-            const int it = its[b] + 1;
-            its[b] = it;
-            if (del < tol || it >= max_iter) done[b] = 1;
-        }
-        __syncwarp();
-    }
-}
-
-// stable compaction of the row map (one CTA): map_out = the entries of map_in whose sample is still running
-__global__ void __launch_bounds__(1024) k_tiled_compact(int M, const int* __restrict__ map_in, const int* __restrict__ done,
-                                                        int* __restrict__ map_out, int* __restrict__ count) {
-    __shared__ int warp_tot[32];
+// compaction of the row map: map_out = the entries of map_in whose sample is still running (block order by arrival:
+// the order of the rows has no influence on any result).  *count must be zero on entry.
+__global__ void __launch_bounds__(256) k_tiled_compact(int M, const int* __restrict__ map_in, const int* __restrict__ done,
+                                                       int* __restrict__ map_out, int* __restrict__ count) {
+    __shared__ int warp_off[8];
     __shared__ int base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) base = 0;
+    const long a = (long)blockIdx.x * 256 + tid;
+    const int b = a < M ? map_in[a] : -1;
+    const bool keep = b >= 0 && !done[b];
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_off[warp] = __popc(m);
     __syncthreads();
-    for (int start = 0; start < M; start += 1024) {
-        const int a = start + tid;
-        const int b = a < M ? map_in[a] : -1;
-        const bool keep = b >= 0 && !done[b];
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) warp_tot[warp] = __popc(m);
-        __syncthreads();
-        int off = base;
-        for (int w = 0; w < warp; ++w) off += warp_tot[w];
-        if (keep) map_out[off + __popc(m & ((1u << lane) - 1u))] = b;
-        __syncthreads();
-        if (tid == 0) {
-            int t = 0;
-            for (int w = 0; w < 32; ++w) t += warp_tot[w];
-            base += t;
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) {
+            const int c = warp_off[w];
+            warp_off[w] = t;
+            t += c;
         }
-        __syncthreads();
+        base = t ? atomicAdd(count, t) : 0;
     }
-    if (tid == 0) *count = base;
+    __syncthreads();
+    if (keep) map_out[base + warp_off[warp] + __popc(m & ((1u << lane) - 1u))] = b;
 }
 
 __global__ void k_tiled_finish(int d, int B, const double* __restrict__ H, const int* __restrict__ its,
@@ -192,27 +125,21 @@ int launch_mle_tiled(const qpb_state_plan* plan, int B, const int32_t* counts, c
 
     k_tiled_init<<<(B + 7) / 8, 256, 0, st>>>(d, K, B, counts, rho0, F, H, H2, map0, its, done);
     QPB_LAUNCHED("k_tiled_init");
-    const int uw = d >= 16 ? 8 : 8;
-    const size_t usmem = sizeof(double) * 5 * (size_t)D * uw;
-    if (usmem > 48 * 1024)
-        QPB_CUDA(cudaFuncSetAttribute(k_tiled_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
     int M = B;
     int* map = map0;
     int* other = map1;
     for (int done_its = 0; done_its < max_iter && M > 0; done_its += kChunk) {
         const int steps = max_iter - done_its < kChunk ? max_iter - done_its : kChunk;
-        long ublocks = ((long)M + uw - 1) / uw;
-        const long cap = (long)num_sms() * 4;
-        if (ublocks > cap) ublocks = cap;
         for (int s = 0; s < steps; ++s) {
             int rc = launch_gemm_f64(M, K, D, H2, map, F, plan->ArT, W, st);
             if (rc != QPB_OK) return rc;
             rc = launch_gemm_f64(M, D, K, W, nullptr, nullptr, plan->Ar, R, st);
             if (rc != QPB_OK) return rc;
-            k_tiled_update<<<(int)ublocks, uw * 32, usmem, st>>>(d, M, map, R, H, H2, its, done, max_iter, tol);
-            QPB_LAUNCHED("k_tiled_update");
+            rc = launch_rrr_update_mat(plan->n, M, map, R, H, H2, its, done, max_iter, tol, st);
+            if (rc != QPB_OK) return rc;
         }
-        k_tiled_compact<<<1, 1024, 0, st>>>(M, map, done, other, count);
+        QPB_CUDA(cudaMemsetAsync(count, 0, sizeof(int), st));
+        k_tiled_compact<<<(M + 255) / 256, 256, 0, st>>>(M, map, done, other, count);
         QPB_LAUNCHED("k_tiled_compact");
         int m_host = 0;
         QPB_CUDA(cudaMemcpyAsync(&m_host, count, sizeof(int), cudaMemcpyDeviceToHost, st));
