@@ -128,6 +128,20 @@ QPB_API int qpb_lin_project(const qpb_state_plan* plan, int B, const int32_t* co
 QPB_API int qpb_mle_rrr(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0, int max_iter,
                 double tol, double* rho, int32_t* iters, void* stream);
 
+/* The same two steps with a START ORDER between them.  R.rho.R iteration counts are heavy-tailed and the persistent
+ * kernels hand samples to their lanes through a queue; a launch ends sooner when the likely long runners start
+ * first.  qpb_lin_project_ordered (physical = 1 implied: the BFGS / R.rho.R start of state.py:209) also returns
+ * that order, judged by the smallest eigenvalue of the unprojected estimate: small positive first, negative (start
+ * state on the boundary, fast) last; the identity when the plan's kernels make no use of it.
+ * qpb_mle_rrr_ordered takes the samples from the queue in that order (NULL = index order).  The order is a
+ * scheduling hint only: every sample's iterates, iteration count and result are bit-identical to qpb_mle_rrr's.
+ * qpb_bootstrap_state does this internally. */
+QPB_API int qpb_lin_project_ordered(const qpb_state_plan* plan, int B, const int32_t* counts, double* rho,
+                            int32_t* order, void* stream);
+QPB_API int qpb_mle_rrr_ordered(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0,
+                        const int32_t* order, int max_iter, double tol, double* rho, int32_t* iters, void* stream);
+QPB_API int qpb_identity_order(int B, int32_t* order, void* stream);
+
 /* Which R.rho.R kernel qpb_mle_rrr dispatches to for this plan (bench.py uses it to count flops):
  * GENERIC: warp per sample, any n<=4 | SMALL: thread per sample, table in shared memory |
  * CONST: thread per sample, table in constant bank, unrolled | PAULI2: two-qubit Pauli-axis POVM, no table |

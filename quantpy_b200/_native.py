@@ -33,6 +33,9 @@ SIGNATURES = {
     "qpb_last_error": (ctypes.c_char_p, []),
     "qpb_launch_count": (ctypes.c_int64, []),
     "qpb_debug_set_trace": (_int, [_vp, ctypes.c_size_t]),
+    "qpb_lin_project_ordered": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
+    "qpb_mle_rrr_ordered": (_int, [_vp, _int, _vp, _vp, _vp, _int, _dbl, _vp, _vp, _vp]),
+    "qpb_identity_order": (_int, [_int, _vp, _vp]),
     "qpb_reset_launch_count": (None, []),
     "qpb_set_option": (_int, [_int, _int]),
     "qpb_get_option": (_int, [_int]),

@@ -25,6 +25,37 @@ int qpb_mle_rrr(const qpb_state_plan* plan, int B, const int32_t* counts, const 
     return rc;
 }
 
+int qpb_lin_project_ordered(const qpb_state_plan* plan, int B, const int32_t* counts, double* rho, int32_t* order,
+                            void* stream) {
+    QPB_REQUIRE(plan != nullptr, "plan is NULL");
+    QPB_REQUIRE(B >= 0, "negative batch");
+    if (B == 0) return QPB_OK;
+    QPB_REQUIRE(counts && rho && order, "NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int* dev_order = nullptr;
+    int rc = launch_lin_project_small(plan, B, counts, 1, rho, st, &dev_order);
+    if (rc == QPB_ERR_UNSUPPORTED) rc = qpb_lin_project(plan, B, counts, 1, rho, stream);
+    if (rc != QPB_OK) return rc;
+    if (dev_order) {
+        QPB_CUDA(cudaMemcpyAsync(order, dev_order, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice, st));
+        return QPB_OK;
+    }
+    return qpb_identity_order(B, order, stream);
+}
+
+int qpb_mle_rrr_ordered(const qpb_state_plan* plan, int B, const int32_t* counts, const double* rho0,
+                        const int32_t* order, int max_iter, double tol, double* rho, int32_t* iters, void* stream) {
+    QPB_REQUIRE(plan != nullptr, "plan is NULL");
+    QPB_REQUIRE(B >= 0 && max_iter >= 0, "bad arguments B=%d max_iter=%d", B, max_iter);
+    QPB_REQUIRE(tol >= 0.0, "tol must be non-negative");
+    if (B == 0) return QPB_OK;
+    QPB_REQUIRE(counts && rho, "NULL buffer");
+    if (order && max_iter > 0 && mle_variant(plan) == QPB_MLE_PAULI2)
+        return launch_mle_small(plan, B, counts, rho0, max_iter, tol, rho, iters, (cudaStream_t)stream, nullptr, nullptr,
+                                nullptr, 1, order);
+    return qpb_mle_rrr(plan, B, counts, rho0, max_iter, tol, rho, iters, stream);  // the other kernels take no hint
+}
+
 int qpb_mle_variant(const qpb_state_plan* plan) {
     QPB_REQUIRE(plan != nullptr, "plan is NULL");
     return mle_variant(plan);

@@ -231,6 +231,22 @@ __device__ __forceinline__ double lin_project_one(int K, long b, const double* _
     return mineig;
 }
 
+__global__ void k_identity_order(int B, int* __restrict__ order) {
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) order[b] = (int)b;
+}
+
+}  // namespace qpb
+
+extern "C" int qpb_identity_order(int B, int32_t* order, void* stream) {
+    if (B <= 0) return QPB_OK;
+    qpb::k_identity_order<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(B, order);
+    QPB_LAUNCHED("k_identity_order");
+    return QPB_OK;
+}
+
+namespace qpb {
+
 int launch_lin_project_small(const qpb_state_plan* plan, int B, const int32_t* counts, int physical, double* rho,
                              cudaStream_t st, const int** order_out) {
     if (order_out) *order_out = nullptr;

@@ -104,15 +104,29 @@ class StatePlan:
                                            nt.stream_ptr()))
         return rho
 
-    def mle(self, counts, rho0=None, max_iter=100, tol=1e-3):
-        """R.rho.R maximum likelihood -> (rho [B, d, d, 2], iters [B] int32) on the device."""
+    def lin_ordered(self, counts):
+        """Physical linear estimates plus the start order for `mle` (qpb_lin_project_ordered)."""
+        torch = nt.torch_cuda()
+        if self.L_dev is None:
+            raise nt.NativeError("plan was built without the linear-inversion table")
+        counts = counts.reshape(-1, self.K).contiguous()
+        B = counts.shape[0]
+        rho = torch.empty((B, self.d, self.d, 2), dtype=torch.float64, device="cuda")
+        order = torch.empty((B,), dtype=torch.int32, device="cuda")
+        nt.check(self._lib.qpb_lin_project_ordered(self.handle, B, nt.ptr(counts), nt.ptr(rho), nt.ptr(order),
+                                                   nt.stream_ptr()))
+        return rho, order
+
+    def mle(self, counts, rho0=None, max_iter=100, tol=1e-3, order=None):
+        """R.rho.R maximum likelihood -> (rho [B, d, d, 2], iters [B] int32) on the device.  `order` (from
+        `lin_ordered`) is a scheduling hint only."""
         torch = nt.torch_cuda()
         counts = counts.reshape(-1, self.K).contiguous()
         B = counts.shape[0]
         rho = torch.empty((B, self.d, self.d, 2), dtype=torch.float64, device="cuda")
         iters = torch.empty((B,), dtype=torch.int32, device="cuda")
-        nt.check(self._lib.qpb_mle_rrr(self.handle, B, nt.ptr(counts), nt.ptr(rho0), int(max_iter), float(tol),
-                                       nt.ptr(rho), nt.ptr(iters), nt.stream_ptr()))
+        nt.check(self._lib.qpb_mle_rrr_ordered(self.handle, B, nt.ptr(counts), nt.ptr(rho0), nt.ptr(order), int(max_iter),
+                                               float(tol), nt.ptr(rho), nt.ptr(iters), nt.stream_ptr()))
         return rho, iters
 
     def estimate(self, counts, method="lin", physical=True, init="lin", max_iter=100, tol=1e-3):
@@ -120,13 +134,14 @@ class StatePlan:
         if method == "lin":
             return self.lin(counts, physical), None
         if method == "mle":
+            order = None
             if init == "lin":
-                start = self.lin(counts, True)  # state.py:209 -> point_estimate("lin"), physical by default
+                start, order = self.lin_ordered(counts)  # state.py:209 -> point_estimate("lin"), physical by default
             elif init == "mixed":
                 start = None
             else:
                 raise ValueError("Invalid value for argument `init`")
-            return self.mle(counts, start, max_iter, tol)
+            return self.mle(counts, start, max_iter, tol, order)
         raise ValueError("Invalid value for argument `method`")
 
     def bootstrap_buffers(self, n_samples, keep=False):

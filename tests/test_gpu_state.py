@@ -627,3 +627,50 @@ def test_tail_merging_is_bit_identical(qp):
         b, ib = tmg.point_estimate_batch(counts, "mle", max_iter=400, tol=1e-6, return_iters=True)
     assert np.array_equal(ia, ib) and np.array_equal(a, b)
     assert ia.max() == 400 and ia.min() < 50
+
+
+def test_ordered_entry_points_change_no_bit(qp):
+    """qpb_lin_project_ordered returns the physical estimates of qpb_lin_project plus a permutation that puts the
+    samples with a small positive smallest eigenvalue first and the negative ones last; qpb_mle_rrr_ordered gives
+    qpb_mle_rrr's bits."""
+    import torch
+
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    lib = nt.load_library()
+    rho = haar(2, 0)
+    povm = qp.generate_measurement_matrix("proj", 2)
+    plan = engine.state_plan(povm, np.ones(1) * 10000)
+    probs = plan.probabilities(qp.Qobj(rho).bloch)[0]
+    B = 20000
+    counts = plan.sample(probs, B, 3, 0)
+    lin = plan.lin(counts, True)
+    lin2 = torch.empty_like(lin)
+    order = torch.empty((B,), dtype=torch.int32, device="cuda")
+    nt.check(lib.qpb_lin_project_ordered(plan.handle, B, nt.ptr(counts), nt.ptr(lin2), nt.ptr(order), nt.stream_ptr()))
+    assert torch.equal(lin, lin2)
+    o = order.cpu().numpy()
+    assert np.array_equal(np.sort(o), np.arange(B))
+    raw = plan.lin(counts, False).cpu().numpy()
+    raw = raw[..., 0] + 1j * raw[..., 1]
+    mineig = np.linalg.eigvalsh(raw)[:, 0]
+    neg = mineig[o] <= 0
+    first_neg = np.argmax(neg) if neg.any() else B
+    assert neg[first_neg:].all() and not neg[:first_neg].any()          # negative class last
+    pos = mineig[o][:first_neg]
+    assert np.all(pos[1:] >= pos[:-1] * 0.8)                              # ascending up to the class width (2^(1/4))
+    a, ia = torch.empty_like(lin), torch.empty((B,), dtype=torch.int32, device="cuda")
+    b, ib = torch.empty_like(lin), torch.empty((B,), dtype=torch.int32, device="cuda")
+    nt.check(lib.qpb_mle_rrr(plan.handle, B, nt.ptr(counts), nt.ptr(lin), 1000, 1e-6, nt.ptr(a), nt.ptr(ia), nt.stream_ptr()))
+    nt.check(lib.qpb_mle_rrr_ordered(plan.handle, B, nt.ptr(counts), nt.ptr(lin), nt.ptr(order), 1000, 1e-6, nt.ptr(b),
+                                     nt.ptr(ib), nt.stream_ptr()))
+    assert torch.equal(a, b) and torch.equal(ia, ib)
+    # plans whose kernels take no hint: identity order, same results
+    povm3 = qp.generate_measurement_matrix("proj", 3)
+    plan3 = engine.state_plan(povm3, np.ones(1) * 10000)
+    c3 = plan3.sample(plan3.probabilities(qp.Qobj(haar(3, 1)).bloch)[0], 64, 1, 0)
+    l3 = plan3.lin(c3, True)
+    l3b, o3 = torch.empty_like(l3), torch.empty((64,), dtype=torch.int32, device="cuda")
+    nt.check(lib.qpb_lin_project_ordered(plan3.handle, 64, nt.ptr(c3), nt.ptr(l3b), nt.ptr(o3), nt.stream_ptr()))
+    assert torch.equal(l3, l3b) and np.array_equal(o3.cpu().numpy(), np.arange(64))
