@@ -8,6 +8,7 @@
 #include "../../include/quantpy_b200.h"
 #include "common.cuh"
 #include "jacobi.cuh"
+#include "jacobi_rows.cuh"
 #include "plan.h"
 
 #include <cstdlib>
@@ -231,9 +232,263 @@ __global__ void k_cptp(int d, int B, const double* __restrict__ choi_in, int n_i
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The same alternating projection for two-qubit channels (Choi 16 x 16) with the eigen-decomposition in registers:
+// 16 LANES PER MATRIX (two matrices per warp), lane r owns row r.  x, p, q, y live in shared memory by rows (leading
+// dimension 17 complex numbers); the CP step loads the lane's row of herm(y + q) into registers and runs the
+// round-robin Jacobi of jacobi_rows.cuh (column updates local, row exchange and rotations by shuffles), and
+// x' = V max(lam, 1e-12) V^dagger reads the other rows of V as shared-memory broadcasts.  The warp-per-matrix
+// kernel above keeps A and V in shared memory and was latency-bound: 1.75 ms for 1000 channels (4 iterations each).
+// ------------------------------------------------------------------------------------------------
+constexpr int kCptpRowsThreads = 128;
+
+template <int d>
+__global__ void __launch_bounds__(kCptpRowsThreads, 1)
+k_cptp_rows(int B, const double* __restrict__ choi_in, int n_iter, double tol, double check_atol,
+            double* __restrict__ choi_out, int32_t* __restrict__ iters) {
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int s = d * d, G = s, LD = s + 1, MAT = s * LD;
+    static_assert(s == 16, "two matrices per warp");
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int tid = threadIdx.x, lane = tid & 31, gl = tid % G, gbase = lane - gl;
+    const int groups_per_block = kCptpRowsThreads / G;
+    cplx* x = reinterpret_cast<cplx*>(smraw) + (size_t)(tid / G) * 5 * MAT;
+    cplx* p = x + MAT;
+    cplx* q = p + MAT;
+    cplx* y = q + MAT;
+    cplx* z = y + MAT;  // transposition / eigenvector scratch
+    const int qi = gl / d, qa = gl % d;  // row r = (input index i, output index a)
+    const double invd = 1.0 / d;
+    const long stride = (long)gridDim.x * groups_per_block;
+    const long first = (long)blockIdx.x * groups_per_block + tid / G;
+    const long rounds = (B + stride - 1) / stride;  // every group of a warp runs the same number of rounds (full-mask shuffles)
+
+    auto group_sum = [&](double v) {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        return v;
+    };
+    // eigenvalues (and eigenvectors in S.v*) of the Hermitian part of the matrix whose rows are in `m`
+    auto eigh_rows = [&](const cplx* m, RowState<s>& S, bool skip) {
+#pragma unroll
+        for (int c = 0; c < s; ++c) {
+            const cplx a = m[gl * LD + c], t = m[c * LD + gl];
+            S.ar[c] = 0.5 * (a.re + t.re);
+            S.ai[c] = (c == gl) ? 0.0 : 0.5 * (a.im - t.im);
+            S.vr[c] = (c == gl) ? 1.0 : 0.0;
+            S.vi[c] = 0.0;
+        }
+        bool done = skip;
+        for (int sweep = 0; sweep < 40; ++sweep) {
+            double off = 0.0, fro = 0.0;
+#pragma unroll
+            for (int c = 0; c < s; ++c) {
+                const double m2 = S.ar[c] * S.ar[c] + S.ai[c] * S.ai[c];
+                fro += m2;
+                if (c != gl) off += m2;
+            }
+            off = group_sum(off);
+            fro = group_sum(fro);
+            if (off <= 1e-30 * fro || fro == 0.0) done = true;
+            if (__all_sync(kFull, done)) break;
+            const double tiny2 = 1e-36 * fro;
+#pragma unroll 1
+            for (int round = 0; round < s - 1; ++round) jacobi_round<s>(S, gl, gbase, done, tiny2);
+        }
+    };
+
+    for (long rnd = 0; rnd < rounds; ++rnd) {
+        const long b = first + rnd * stride;
+        const bool valid = b < B;
+        __syncwarp();
+        {
+            const cplx* src = reinterpret_cast<const cplx*>(choi_in) + (valid ? b : 0) * s * s + gl * s;
+#pragma unroll
+            for (int c = 0; c < s; ++c) {
+                cplx v;
+                v.re = (c == gl) ? invd : 0.0;
+                v.im = 0.0;
+                if (valid) v = src[c];
+                x[gl * LD + c] = v;
+                p[gl * LD + c].re = p[gl * LD + c].im = 0.0;
+                q[gl * LD + c].re = q[gl * LD + c].im = 0.0;
+                y[gl * LD + c].re = y[gl * LD + c].im = 0.0;
+            }
+        }
+        __syncwarp();
+        bool active = valid;
+        int it = 0;
+        auto store_result = [&]() {
+            cplx* dst = reinterpret_cast<cplx*>(choi_out) + b * s * s + gl * s;
+#pragma unroll
+            for (int c = 0; c < s; ++c) dst[c] = x[gl * LD + c];
+        };
+        if (check_atol >= 0.0) {
+            // Channel.is_cptp (channel.py:144-157): |Tr_out x - I| <= atol + 1e-5 |I| elementwise, eigenvalues >= -atol
+            double bad = 0.0;
+            double tre[d], tim[d];
+#pragma unroll
+            for (int j = 0; j < d; ++j) {
+                const cplx v = x[gl * LD + j * d + qa];
+                tre[j] = v.re;
+                tim[j] = v.im;
+            }
+#pragma unroll
+            for (int o = 1; o < d; o <<= 1)
+#pragma unroll
+                for (int j = 0; j < d; ++j) {
+                    tre[j] += __shfl_xor_sync(kFull, tre[j], o);
+                    tim[j] += __shfl_xor_sync(kFull, tim[j], o);
+                }
+#pragma unroll
+            for (int j = 0; j < d; ++j) {
+                const double target = (qi == j) ? 1.0 : 0.0;
+                const double dev = sqrt((tre[j] - target) * (tre[j] - target) + tim[j] * tim[j]);
+                if (dev > check_atol + 1e-5 * target) bad = 1.0;
+            }
+            RowState<s> S;
+            eigh_rows(x, S, !valid);
+            double lam_own = 0.0;
+#pragma unroll
+            for (int c = 0; c < s; ++c)
+                if (c == gl) lam_own = S.ar[c];
+            if (lam_own < -check_atol) bad = 1.0;
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) bad = fmax(bad, __shfl_xor_sync(kFull, bad, o));
+            if (active && bad == 0.0) {
+                store_result();
+                active = false;
+            }
+        }
+        for (int iter = 1; iter <= n_iter; ++iter) {
+            if (!__any_sync(kFull, active)) break;
+            // ---- y' = TP(x + p) = t + ((I - Tr_out t) (x) I) / d
+            double tr_[s], ti_[s];
+#pragma unroll
+            for (int c = 0; c < s; ++c) {
+                tr_[c] = x[gl * LD + c].re + p[gl * LD + c].re;
+                ti_[c] = x[gl * LD + c].im + p[gl * LD + c].im;
+            }
+            double gre[d], gim[d];  // sum over the output index a of t[(i,a)][(j,a)]: the four lanes of quad i
+#pragma unroll
+            for (int j = 0; j < d; ++j) {
+                gre[j] = 0.0;
+                gim[j] = 0.0;
+#pragma unroll
+                for (int c = 0; c < s; ++c)
+                    if (c / d == j && c % d == qa) {
+                        gre[j] = tr_[c];
+                        gim[j] = ti_[c];
+                    }
+            }
+#pragma unroll
+            for (int o = 1; o < d; o <<= 1)
+#pragma unroll
+                for (int j = 0; j < d; ++j) {
+                    gre[j] += __shfl_xor_sync(kFull, gre[j], o);
+                    gim[j] += __shfl_xor_sync(kFull, gim[j], o);
+                }
+            double c1r = 0.0, c1i = 0.0;
+#pragma unroll
+            for (int c = 0; c < s; ++c) {
+                double yr = tr_[c], yi = ti_[c];
+                if (c % d == qa) {
+                    const int j = c / d;
+                    yr += (((qi == j) ? 1.0 : 0.0) - gre[j]) * invd;
+                    yi += -gim[j] * invd;
+                }
+                const cplx yo = y[gl * LD + c], qq = q[gl * LD + c];
+                const double dr = yr - yo.re, di = yi - yo.im;
+                c1r += dr * qq.re + di * qq.im;  // conj(y_diff) * q
+                c1i += dr * qq.im - di * qq.re;
+                y[gl * LD + c].re = yr;
+                y[gl * LD + c].im = yi;
+                z[gl * LD + c].re = yr + qq.re;  // y' + q, Hermitised by eigh_rows
+                z[gl * LD + c].im = yi + qq.im;
+            }
+            __syncwarp();
+            // ---- x' = CP(y' + q): eigh, clip at 1e-12, recompose
+            RowState<s> S;
+            eigh_rows(z, S, !active);
+            double lam_own = 0.0;
+#pragma unroll
+            for (int c = 0; c < s; ++c)
+                if (c == gl) lam_own = S.ar[c];
+            lam_own = fmax(lam_own, kClipChoi);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < s; ++j) {  // z <- V (rows)
+                z[gl * LD + j].re = S.vr[j];
+                z[gl * LD + j].im = S.vi[j];
+            }
+            double wr[s], wi[s];  // lam_j V_rj
+#pragma unroll
+            for (int j = 0; j < s; ++j) {
+                const double lam = __shfl_sync(kFull, lam_own, gbase + j);
+                wr[j] = lam * S.vr[j];
+                wi[j] = lam * S.vi[j];
+            }
+            __syncwarp();
+            double c2r = 0.0, c2i = 0.0, c3 = 0.0;
+#pragma unroll 4
+            for (int c = 0; c < s; ++c) {
+                double re = 0.0, im = 0.0;
+#pragma unroll
+                for (int j = 0; j < s; ++j) {
+                    const cplx v = z[c * LD + j];  // the same address for all lanes of the group: a broadcast
+                    re += wr[j] * v.re + wi[j] * v.im;
+                    im += wi[j] * v.re - wr[j] * v.im;
+                }
+                const cplx xo = x[gl * LD + c], pp = p[gl * LD + c], yy = y[gl * LD + c];
+                const double dr = re - xo.re, di = im - xo.im;
+                c2r += dr * pp.re + di * pp.im;
+                c2i += dr * pp.im - di * pp.re;
+                const double pr = re - yy.re, pi = im - yy.im;  // p_diff = x' - y'
+                if (active) {
+                    x[gl * LD + c].re = re;
+                    x[gl * LD + c].im = im;
+                    p[gl * LD + c].re = pp.re + pr;
+                    p[gl * LD + c].im = pp.im + pi;
+                    q[gl * LD + c].re -= pr;
+                    q[gl * LD + c].im -= pi;
+                }
+                c3 += pr * pr + pi * pi;
+            }
+            c1r = group_sum(c1r);
+            c1i = group_sum(c1i);
+            c2r = group_sum(c2r);
+            c2i = group_sum(c2i);
+            c3 = group_sum(c3);
+            __syncwarp();
+            const double crit = 2.0 * (sqrt(c1r * c1r + c1i * c1i) + sqrt(c2r * c2r + c2i * c2i)) + 2.0 * c3;
+            if (active) {
+                it = iter;
+                if (crit < tol) {
+                    store_result();
+                    active = false;
+                }
+            }
+        }
+        if (active) store_result();  // iteration cap reached (or n_iter == 0)
+        if (valid && iters && gl == 0) iters[b] = it;
+    }
+}
+
 static int launch_cptp(int n, int B, const double* in, int n_iter, double tol, double check_atol, double* out,
                        int32_t* iters, cudaStream_t st) {
     const int d = 1 << n, s = d * d;
+    if (s == 16 && !option(QPB_OPT_NO_ROW_JACOBI)) {
+        const int groups = kCptpRowsThreads / 16;
+        const size_t rsmem = sizeof(cplx) * 5 * 16 * 17 * (size_t)groups;
+        QPB_CUDA(cudaFuncSetAttribute(k_cptp_rows<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+        long rblocks = ((long)B + groups - 1) / groups;
+        const long rcap = (long)num_sms();
+        if (rblocks > rcap) rblocks = rcap;
+        k_cptp_rows<4><<<(int)rblocks, kCptpRowsThreads, rsmem, st>>>(B, in, n_iter, tol, check_atol, out, iters);
+        QPB_LAUNCHED("k_cptp_rows");
+        return QPB_OK;
+    }
     const int warps = (s >= 16) ? 4 : 8;
     const size_t smem = warps * cptp_smem_per_warp(s);
     QPB_REQUIRE(smem <= 227 * 1024, "CPTP projection needs %zu bytes of shared memory", smem);
