@@ -131,8 +131,9 @@ QPB_API int qpb_mle_rrr(const qpb_state_plan* plan, int B, const int32_t* counts
 /* The same two steps with a START ORDER between them.  R.rho.R iteration counts are heavy-tailed and the persistent
  * kernels hand samples to their lanes through a queue; a launch ends sooner when the likely long runners start
  * first.  qpb_lin_project_ordered (physical = 1 implied: the BFGS / R.rho.R start of state.py:209) also returns
- * that order, judged by the smallest eigenvalue of the unprojected estimate: small positive first, negative (start
- * state on the boundary, fast) last; the identity when the plan's kernels make no use of it.
+ * that order: ascending smallest POSITIVE eigenvalue of the unprojected estimate (the smaller, the longer the
+ * iteration tends to run; negative eigenvalues are clipped by the projection and do not count); the identity when the
+ * plan's kernels make no use of it.
  * qpb_mle_rrr_ordered takes the samples from the queue in that order (NULL = index order).  The order is a
  * scheduling hint only: every sample's iterates, iteration count and result are bit-identical to qpb_mle_rrr's.
  * qpb_bootstrap_state does this internally. */
