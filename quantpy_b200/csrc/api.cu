@@ -93,7 +93,8 @@ static const char* const kOptionEnv[QPB_OPT_COUNT_] = {
     "QPB_MLE_BLOCKS_PER_SM", "QPB_MLE_LANES", "QPB_NO_TILED_MLE",
     "QPB_MLE_PARK_AGE", "QPB_MLE_PARK_LIVE", "QPB_MLE_W_WARPS", "QPB_MLE_PARK_PLATEAU", "QPB_NO_TMA_GEMM",
     "QPB_MLE_TAIL_POLL", "QPB_MLE_TAIL_AGE", "QPB_MLE_ADOPT", "QPB_MLE_MERGE", "QPB_NO_MLE_ORDER",
-    "QPB_MLE_PARK_AGE_LO", "QPB_MLE_PARK_AGE_PCT", "QPB_MLE_PARK_AGE_END", "QPB_MLE_PARK_AGE_PCT2"};
+    "QPB_MLE_PARK_AGE_LO", "QPB_MLE_PARK_AGE_PCT", "QPB_MLE_PARK_AGE_END", "QPB_MLE_PARK_AGE_PCT2",
+    "QPB_MLE_REFILL_MIN"};
 static const bool g_options_loaded = [] {
     for (int i = 0; i < QPB_OPT_COUNT_; ++i) {
         const char* e = kOptionEnv[i] ? getenv(kOptionEnv[i]) : nullptr;

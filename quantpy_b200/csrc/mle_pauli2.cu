@@ -127,6 +127,8 @@ struct Pauli2Args {
                           // entries waiting -> its free lanes adopt them
     int tail_age;         // ... samples younger than this stay where they are
     int adopt;            // free lanes of a drained warp adopt waiting entries (0: W workers only)
+    int refill_min;       // lanes without a sample wait until this many of the warp are free (one refill = one queue atomic
+                          // and ~1500 cycles of load latency for the whole warp); 1: refill at once
     int merge;            // drained thread-per-sample warps of a CTA pack their samples into fewer warps (0: off)
     long long* trace_s;   // profiling: 4 words per sample (start, hand-over, pick-up, finish times), or null
     long long* trace;     // profiling (qpb_debug_set_trace): 16 words per warp, see tools/pauli2_trace.py; normally null
@@ -769,7 +771,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
         // ---- refill lanes without work -------------------------------------------------------
         const bool want = alive && b < 0;
         const unsigned need = __ballot_sync(0xffffffffu, want);
-        if (need) {
+        if (need && (__popc(need) >= a.refill_min || __ballot_sync(0xffffffffu, b >= 0) == 0)) {
             unsigned base = 0;
             const int leader = __ffs(need) - 1;
             if (lane == leader) base = atomicAdd(&a.ctrl[0], (unsigned)__popc(need));
@@ -1153,6 +1155,7 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
         a.park_live = 0;
         a.park_plateau = 0;
         a.tail_poll = a.tail_age = a.adopt = a.merge = 0;
+        a.refill_min = 1;
         // warps per CTA: enough that every SM has work, at most 32 (profiling: MLE_BLOCKS_PER_SM overrides)
         int dw = option(QPB_OPT_MLE_BLOCKS_PER_SM) > 0 ? option(QPB_OPT_MLE_BLOCKS_PER_SM) : (int)(((long long)B + sms - 1) / sms);
         const int dw_max = option(QPB_OPT_MLE_W_WARPS) > 4 ? option(QPB_OPT_MLE_W_WARPS) : 16;  // profiling: 16 | 24 | 32
@@ -1181,6 +1184,7 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
             a.park_live = 0;
             a.park_plateau = 0;
             a.tail_poll = a.tail_age = a.adopt = a.merge = 0;
+            a.refill_min = 1;
             w_warps = 0;
             a.single_warps = kPauliThreadsSingle / 32;
         } else {
@@ -1215,6 +1219,8 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
             a.tail_age = option(QPB_OPT_MLE_TAIL_AGE) > 0 ? option(QPB_OPT_MLE_TAIL_AGE) : 150;
             const int ad = option(QPB_OPT_MLE_ADOPT);
             a.adopt = ad <= 0 ? 0 : ad;      // measured: no gain, off by default
+            // measured (tools/pauli2_sweep_j.py, 1e5): 1 -> 1.745, 2 -> 1.708, 3 -> 1.689, 4 -> 1.687, 8 -> 1.693 ms per step
+            a.refill_min = option(QPB_OPT_MLE_REFILL_MIN) > 0 ? option(QPB_OPT_MLE_REFILL_MIN) : 4;
             const int mg = option(QPB_OPT_MLE_MERGE);
             a.merge = mg <= 0 ? 0 : mg;      // measured: fuller warps, but the launch ends later (the packed warps keep
                                              // long runners on the slow mapping); off by default
