@@ -767,11 +767,42 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
     const double tol2 = a.tol * a.tol;
     const bool hand_over = a.single_warps < (int)(blockDim.x >> 5) || a.park_live > 0 || a.park_age < 0x7fffffff;
 
+    // write the results of finished samples whose lanes satisfy `now` (warp-uniform call, divergent body)
+    auto write_back = [&](bool now) {
+        const bool wb = now && b < -1;
+        const unsigned wbm = __ballot_sync(0xffffffffu, wb);
+        if (wbm == 0) return;
+        if (wb) {
+            const long long ob = -2 - b;
+            if (a.rho) {
+                double2* out = reinterpret_cast<double2*>(a.rho) + ob * D;
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) {
+                        double2 z;
+                        z.x = x <= y ? h[x * 4 + y] : h[y * 4 + x];
+                        z.y = x == y ? 0.0 : (x < y ? h[y * 4 + x] : -h[x * 4 + y]);
+                        out[x * 4 + y] = z;
+                    }
+            }
+            if (a.hs_dist) a.hs_dist[ob] = hs_distance_packed(h, a.hs_ref);
+            if (a.iters) a.iters[ob] = it;
+            if (a.trace_s) a.trace_s[4 * ob + 3] = (long long)globaltimer_ns();
+            b = -1;
+        }
+        if (hand_over && lane == 0) atomicAdd(&a.ctrl[3], (unsigned)__popc(wbm));
+    };
+
     while (true) {
         // ---- refill lanes without work -------------------------------------------------------
         const bool want = alive && b < 0;
         const unsigned need = __ballot_sync(0xffffffffu, want);
-        if (need && (__popc(need) >= a.refill_min || __ballot_sync(0xffffffffu, b >= 0) == 0)) {
+        const bool go = need && (__popc(need) >= a.refill_min || __ballot_sync(0xffffffffu, b >= 0) == 0);
+        // results of finished samples (b = -2 - index, state still in h) are written together with the refill, or at
+        // once by lanes that will not get another sample
+        write_back(go || !alive);
+        if (go) {
             unsigned base = 0;
             const int leader = __ffs(need) - 1;
             if (lane == leader) base = atomicAdd(&a.ctrl[0], (unsigned)__popc(need));
@@ -813,6 +844,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
         const bool drained = __any_sync(0xffffffffu, !alive);
         if (active == 0 && !drained) continue;  // cannot happen (a lane without work either refilled or saw the end)
         if (a.merge && drained) {
+            write_back(true);  // free lanes are about to be overwritten
             const unsigned full = 0xffffffffu;
             auto lock = [&]() {
                 if (lane == 0)
@@ -930,6 +962,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
             bool park = b >= 0 && ((!tail && it >= my_age) || plateau);
             if (drained && __popc(active) <= a.park_live) park = b >= 0;
             if (tail && ((++tick) & (a.tail_poll - 1)) == 0 && __popc(active) > a.park_live) {
+                write_back(a.adopt > 0);  // free lanes may adopt entries
                 // the queue is empty: look at the hand-over list.  waiting > 0: W workers without an entry -> give
                 // them this warp's oldest sample; waiting < 0: entries without a worker -> free lanes adopt them.
                 unsigned r = 0, t = 0;
@@ -1015,28 +1048,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
                 }
             }
         }
-        if (finished) {
-            if (a.rho) {
-                double2* out = reinterpret_cast<double2*>(a.rho) + b * D;
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        double2 z;
-                        z.x = x <= y ? h[x * 4 + y] : h[y * 4 + x];
-                        z.y = x == y ? 0.0 : (x < y ? h[y * 4 + x] : -h[x * 4 + y]);
-                        out[x * 4 + y] = z;
-                    }
-            }
-            if (a.hs_dist) a.hs_dist[b] = hs_distance_packed(h, a.hs_ref);
-            if (a.iters) a.iters[b] = it;
-            if (a.trace_s) a.trace_s[4 * b + 3] = (long long)globaltimer_ns();
-            b = -1;
-        }
-        if (hand_over) {
-            const unsigned fin = __ballot_sync(0xffffffffu, finished);
-            if (fin && lane == 0) atomicAdd(&a.ctrl[3], (unsigned)__popc(fin));
-        }
+        if (finished) b = -2 - b;  // result pending: written by write_back()
     }
     if (tr_s && lane == 0) {
         tr_s[2] = (long long)globaltimer_ns();
