@@ -73,7 +73,8 @@ enum {
     QPB_OPT_MLE_PARK_AGE_END = 25, /* ... and falling again for the samples started after the first wave of lanes, down to this age (0 = default: no fall) */
     QPB_OPT_MLE_PARK_AGE_PCT2 = 26,/* ... over this percentage of the remaining queue (0 = default) */
     QPB_OPT_MLE_REFILL_MIN = 27,   /* pauli2 MLE tuning: free lanes of a warp wait for this many before they take new samples (0 = default) */
-    QPB_OPT_COUNT_ = 28
+    QPB_OPT_NO_WARM_JACOBI = 28,   /* CPTP projection (Choi 16 x 16): every eigen-decomposition starts from the identity instead of the previous step's eigenvectors */
+    QPB_OPT_COUNT_ = 29
 };
 QPB_API int qpb_set_option(int which, int value);
 QPB_API int qpb_get_option(int which);

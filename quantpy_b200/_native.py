@@ -75,7 +75,7 @@ OPTIONS = {"NO_TAIL_MERGE": 0, "NO_HS_FUSION": 1, "NO_PAULI_KERNEL": 2, "NO_CONS
            "MLE_W_WARPS": 15, "MLE_PARK_PLATEAU": 16, "NO_TMA_GEMM": 17, "MLE_TAIL_POLL": 18, "MLE_TAIL_AGE": 19,
            "MLE_ADOPT": 20, "MLE_MERGE": 21, "NO_MLE_ORDER": 22,
            "MLE_PARK_AGE_LO": 23, "MLE_PARK_AGE_PCT": 24, "MLE_PARK_AGE_END": 25, "MLE_PARK_AGE_PCT2": 26,
-           "MLE_REFILL_MIN": 27}
+           "MLE_REFILL_MIN": 27, "NO_WARM_JACOBI": 28}
 SAMPLERS = {"auto": 0, "alias": 1, "binomial": 2}
 
 

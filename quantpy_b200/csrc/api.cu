@@ -94,7 +94,7 @@ static const char* const kOptionEnv[QPB_OPT_COUNT_] = {
     "QPB_MLE_PARK_AGE", "QPB_MLE_PARK_LIVE", "QPB_MLE_W_WARPS", "QPB_MLE_PARK_PLATEAU", "QPB_NO_TMA_GEMM",
     "QPB_MLE_TAIL_POLL", "QPB_MLE_TAIL_AGE", "QPB_MLE_ADOPT", "QPB_MLE_MERGE", "QPB_NO_MLE_ORDER",
     "QPB_MLE_PARK_AGE_LO", "QPB_MLE_PARK_AGE_PCT", "QPB_MLE_PARK_AGE_END", "QPB_MLE_PARK_AGE_PCT2",
-    "QPB_MLE_REFILL_MIN"};
+    "QPB_MLE_REFILL_MIN", "QPB_NO_WARM_JACOBI"};
 static const bool g_options_loaded = [] {
     for (int i = 0; i < QPB_OPT_COUNT_; ++i) {
         const char* e = kOptionEnv[i] ? getenv(kOptionEnv[i]) : nullptr;
@@ -102,7 +102,7 @@ static const bool g_options_loaded = [] {
         if (e && *e) {
             if (i == QPB_OPT_SAMPLER) v = !strcmp(e, "alias") ? 1 : (!strcmp(e, "binomial") ? 2 : 0);
             else if (i >= QPB_OPT_MLE_BLOCKS_PER_SM && i != QPB_OPT_NO_TILED_MLE && i != QPB_OPT_NO_TMA_GEMM &&
-                     i != QPB_OPT_NO_MLE_ORDER) v = atoi(e);
+                     i != QPB_OPT_NO_MLE_ORDER && i != QPB_OPT_NO_WARM_JACOBI) v = atoi(e);
             else v = 1;
         }
         g_options[i].store(v);

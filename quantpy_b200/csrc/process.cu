@@ -246,18 +246,19 @@ constexpr int kCptpRowsThreads = 128;
 template <int d>
 __global__ void __launch_bounds__(kCptpRowsThreads, 1)
 k_cptp_rows(int B, const double* __restrict__ choi_in, int n_iter, double tol, double check_atol,
-            double* __restrict__ choi_out, int32_t* __restrict__ iters) {
+            double* __restrict__ choi_out, int32_t* __restrict__ iters, int option_cold) {
     constexpr unsigned kFull = 0xffffffffu;
     constexpr int s = d * d, G = s, LD = s + 1, MAT = s * LD;
     static_assert(s == 16, "two matrices per warp");
     extern __shared__ __align__(16) unsigned char smraw[];
     const int tid = threadIdx.x, lane = tid & 31, gl = tid % G, gbase = lane - gl;
     const int groups_per_block = kCptpRowsThreads / G;
-    cplx* x = reinterpret_cast<cplx*>(smraw) + (size_t)(tid / G) * 5 * MAT;
+    cplx* x = reinterpret_cast<cplx*>(smraw) + (size_t)(tid / G) * 6 * MAT;
     cplx* p = x + MAT;
     cplx* q = p + MAT;
     cplx* y = q + MAT;
-    cplx* z = y + MAT;  // transposition / eigenvector scratch
+    cplx* z = y + MAT;  // transposition scratch
+    cplx* vp = z + MAT; // eigenvectors of the last CP step (rows)
     const int qi = gl / d, qa = gl % d;  // row r = (input index i, output index a)
     const double invd = 1.0 / d;
     const long stride = (long)gridDim.x * groups_per_block;
@@ -270,7 +271,11 @@ k_cptp_rows(int B, const double* __restrict__ choi_in, int n_iter, double tol, d
         return v;
     };
     // eigenvalues (and eigenvectors in S.v*) of the Hermitian part of the matrix whose rows are in `m`
-    auto eigh_rows = [&](const cplx* m, RowState<s>& S, bool skip) {
+    // eigenvalues (diagonal of S.a*) and eigenvectors (S.v*, by rows) of the Hermitian part of the matrix whose rows
+    // are in `m`.  warm: vp holds the eigenvectors V0 of a nearby matrix (the previous CP step of the same Dykstra
+    // iteration sequence): the Jacobi then starts from V0^dagger A V0, which is almost diagonal (2-3 sweeps instead of
+    // 7), with the eigenvector accumulator initialised to V0; costs two 16 x 16 products (~1/3 of a sweep).
+    auto eigh_rows = [&](const cplx* m, RowState<s>& S, bool skip, bool warm) {
 #pragma unroll
         for (int c = 0; c < s; ++c) {
             const cplx a = m[gl * LD + c], t = m[c * LD + gl];
@@ -278,6 +283,41 @@ k_cptp_rows(int B, const double* __restrict__ choi_in, int n_iter, double tol, d
             S.ai[c] = (c == gl) ? 0.0 : 0.5 * (a.im - t.im);
             S.vr[c] = (c == gl) ? 1.0 : 0.0;
             S.vi[c] = 0.0;
+        }
+        if (warm) {  // warp-uniform
+            __syncwarp();  // everybody has read m
+            cplx* t1 = const_cast<cplx*>(m);  // T1 = A V0 overwrites m (row gl only)
+#pragma unroll 2
+            for (int j = 0; j < s; ++j) {
+                double re = 0.0, im = 0.0;
+#pragma unroll
+                for (int k = 0; k < s; ++k) {
+                    const cplx v = vp[k * LD + j];
+                    re += S.ar[k] * v.re - S.ai[k] * v.im;
+                    im += S.ar[k] * v.im + S.ai[k] * v.re;
+                }
+                t1[gl * LD + j].re = re;
+                t1[gl * LD + j].im = im;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < s; ++c) S.ar[c] = S.ai[c] = 0.0;
+#pragma unroll 2
+            for (int k = 0; k < s; ++k) {  // A'[gl][c] = sum_k conj(V0[k][gl]) T1[k][c]
+                const cplx u = vp[k * LD + gl];
+#pragma unroll
+                for (int c = 0; c < s; ++c) {
+                    const cplx t = t1[k * LD + c];
+                    S.ar[c] += u.re * t.re + u.im * t.im;
+                    S.ai[c] += u.re * t.im - u.im * t.re;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < s; ++c) {
+                if (c == gl) S.ai[c] = 0.0;
+                S.vr[c] = vp[gl * LD + c].re;
+                S.vi[c] = vp[gl * LD + c].im;
+            }
         }
         bool done = skip;
         for (int sweep = 0; sweep < 40; ++sweep) {
@@ -348,7 +388,7 @@ k_cptp_rows(int B, const double* __restrict__ choi_in, int n_iter, double tol, d
                 if (dev > check_atol + 1e-5 * target) bad = 1.0;
             }
             RowState<s> S;
-            eigh_rows(x, S, !valid);
+            eigh_rows(x, S, !valid, false);
             double lam_own = 0.0;
 #pragma unroll
             for (int c = 0; c < s; ++c)
@@ -410,7 +450,8 @@ k_cptp_rows(int B, const double* __restrict__ choi_in, int n_iter, double tol, d
             __syncwarp();
             // ---- x' = CP(y' + q): eigh, clip at 1e-12, recompose
             RowState<s> S;
-            eigh_rows(z, S, !active);
+            // cold restart every 16 steps: the accumulated V0 loses orthogonality by ~1e-16 per rotation
+            eigh_rows(z, S, !active, iter > 1 && ((iter - 1) & 15) != 0 && !option_cold);
             double lam_own = 0.0;
 #pragma unroll
             for (int c = 0; c < s; ++c)
@@ -418,9 +459,9 @@ k_cptp_rows(int B, const double* __restrict__ choi_in, int n_iter, double tol, d
             lam_own = fmax(lam_own, kClipChoi);
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < s; ++j) {  // z <- V (rows)
-                z[gl * LD + j].re = S.vr[j];
-                z[gl * LD + j].im = S.vi[j];
+            for (int j = 0; j < s; ++j) {  // vp <- V (rows): this step's recomposition, the next step's warm start
+                vp[gl * LD + j].re = S.vr[j];
+                vp[gl * LD + j].im = S.vi[j];
             }
             double wr[s], wi[s];  // lam_j V_rj
 #pragma unroll
@@ -436,7 +477,7 @@ k_cptp_rows(int B, const double* __restrict__ choi_in, int n_iter, double tol, d
                 double re = 0.0, im = 0.0;
 #pragma unroll
                 for (int j = 0; j < s; ++j) {
-                    const cplx v = z[c * LD + j];  // the same address for all lanes of the group: a broadcast
+                    const cplx v = vp[c * LD + j];  // the same address for all lanes of the group: a broadcast
                     re += wr[j] * v.re + wi[j] * v.im;
                     im += wi[j] * v.re - wr[j] * v.im;
                 }
@@ -480,12 +521,13 @@ static int launch_cptp(int n, int B, const double* in, int n_iter, double tol, d
     const int d = 1 << n, s = d * d;
     if (s == 16 && !option(QPB_OPT_NO_ROW_JACOBI)) {
         const int groups = kCptpRowsThreads / 16;
-        const size_t rsmem = sizeof(cplx) * 5 * 16 * 17 * (size_t)groups;
+        const size_t rsmem = sizeof(cplx) * 6 * 16 * 17 * (size_t)groups;
         QPB_CUDA(cudaFuncSetAttribute(k_cptp_rows<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
         long rblocks = ((long)B + groups - 1) / groups;
         const long rcap = (long)num_sms();
         if (rblocks > rcap) rblocks = rcap;
-        k_cptp_rows<4><<<(int)rblocks, kCptpRowsThreads, rsmem, st>>>(B, in, n_iter, tol, check_atol, out, iters);
+        k_cptp_rows<4><<<(int)rblocks, kCptpRowsThreads, rsmem, st>>>(B, in, n_iter, tol, check_atol, out, iters,
+                                                                  option(QPB_OPT_NO_WARM_JACOBI));
         QPB_LAUNCHED("k_cptp_rows");
         return QPB_OK;
     }
