@@ -755,7 +755,7 @@ def measure(gpu, cfg, steps, warmup, e2e_steps, with_cpu, cpu_seconds, with_roof
     rec = {"metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
            "ms_per_step": 1e3 * total_s / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(cfg, world), "gpu_launches": launches,
-           "e2e": e2e}
+           "ms_each": [round(t, 4) for t in step_ms], "e2e": e2e}
     if mean_iters is not None:
         rec["mean_iterations"] = mean_iters
     if with_roofline and rank == 0:
@@ -822,7 +822,7 @@ def run_ours(args, rank, local_rank, world):
         for name in ("c1", "c3", "c4", "c5-1q", "c5-2q"):
             sub = resolve_config(args, name)
             heavy = name in ("c4",)
-            r, _ = measure(gpu, sub, steps=3 if heavy else 5, warmup=3, e2e_steps=2 if heavy else 3,
+            r, _ = measure(gpu, sub, steps=3 if heavy else 10, warmup=3, e2e_steps=2 if heavy else 5,
                            with_cpu=not args.no_cpu_baseline, cpu_seconds=4.0)
             r["name"] = name
             others.append(r)

@@ -234,8 +234,9 @@ class BootstrapProcessInterval(ConfidenceInterval):
         lo, hi = parallel.shard_bounds(self.n_points, rank, size)
         seed = parallel.broadcast_seed(engine.next_seed()) if seed is None else int(seed)
         first = self.tmg.tomographs[0]
-        boot = self.tmg.__class__(self.channel, self.tmg.input_states, self.tmg.dst)
-        boot.adopt_measurement(first.povm_matrix, first.n_measurements)  # tables only: no sampling, no RNG draw
+        # same input basis, POVM tables and shot bookkeeping, another channel: no sampling, no RNG draw, no
+        # re-derivation of the basis decompositions (the batch estimators read only POVM and shots from `tomographs`)
+        boot = self.tmg._with_channel(self.channel)
         centre = self.channel.choi.matrix
         kind = dst_kind(self.tmg.dst)
         torch = nt.torch_cuda()
