@@ -707,6 +707,12 @@ def measure(gpu, cfg, steps, warmup, e2e_steps, with_cpu, cpu_seconds, with_roof
     B = wl.B
     for i in range(warmup):
         wl.step(i)
+    # a config measured after a CPU-only phase (the previous config's cpu_baseline leg) finds the SM clock at idle:
+    # keep the device busy for 50 ms more (untimed) so that the timed steps run at the clock the `clocks` key reports
+    t_busy = time.perf_counter() + 0.05
+    while time.perf_counter() < t_busy:
+        wl.step(0)
+        torch.cuda.synchronize()
     gpu.barrier()
     lib.qpb_reset_launch_count()
     evs = gpu.event_pairs(steps)

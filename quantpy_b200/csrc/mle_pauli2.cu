@@ -1205,7 +1205,7 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
             // measured on B200 (tools/pauli2_sweep_d.py, C2 workload): the fuller the thread-per-sample lanes, the
             // less W capacity is left, so the hand-over age rises with the batch: 200 / 300 / 450 iterations
             const long long lanes = (long long)sms * kPauliThreadsSingle;
-            const int age = (long long)B * 2 <= lanes ? 200 : ((long long)B * 2 <= lanes * 3 ? 300 : 450);
+            const int age = (long long)B * 2 <= lanes ? 200 : ((long long)B * 2 <= lanes * 3 ? 300 : 500);
             a.park_age = option(QPB_OPT_MLE_PARK_AGE) > 0 ? option(QPB_OPT_MLE_PARK_AGE) : age;
             {
                 // measured on B200 (tools/pauli2_sweep_h.py): while most of the batch starts in the first wave of
@@ -1226,13 +1226,15 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
             a.park_live = option(QPB_OPT_MLE_PARK_LIVE) > 0 ? option(QPB_OPT_MLE_PARK_LIVE) : ((long long)B * 4 <= lanes ? 16 : 5);
             if (a.single_warps < kPauliThreadsSingle / 32) w_warps = 12 - a.single_warps;
             const int poll = option(QPB_OPT_MLE_TAIL_POLL);
-            a.tail_poll = poll < 0 ? 0 : (poll == 0 ? ((long long)B <= lanes ? 4 : 0) : poll);  // below one wave the W workers idle early
+            a.tail_poll = poll < 0 ? 0 : (poll == 0 ? 4 : poll);
             while (a.tail_poll & (a.tail_poll - 1)) a.tail_poll &= a.tail_poll - 1;  // power of two
             a.tail_age = option(QPB_OPT_MLE_TAIL_AGE) > 0 ? option(QPB_OPT_MLE_TAIL_AGE) : 150;
             const int ad = option(QPB_OPT_MLE_ADOPT);
             a.adopt = ad <= 0 ? 0 : ad;      // measured: no gain, off by default
             // measured (tools/pauli2_sweep_j.py, 1e5): 1 -> 1.745, 2 -> 1.708, 3 -> 1.689, 4 -> 1.687, 8 -> 1.693 ms per step
-            a.refill_min = option(QPB_OPT_MLE_REFILL_MIN) > 0 ? option(QPB_OPT_MLE_REFILL_MIN) : 4;
+            a.refill_min = option(QPB_OPT_MLE_REFILL_MIN) > 0 ? option(QPB_OPT_MLE_REFILL_MIN) : 6;
+            // (with the write-back deferred to the refill, tools/pauli2_sweep_k.py: 4 -> 1.587, 6 -> 1.580 ms; hand-over age
+            // 450 ... 700 and the demand-driven tail within 1 % of each other)
             const int mg = option(QPB_OPT_MLE_MERGE);
             a.merge = mg <= 0 ? 0 : mg;      // measured: fuller warps, but the launch ends later (the packed warps keep
                                              // long runners on the slow mapping); off by default
