@@ -1,5 +1,7 @@
 """GPU tests of the fused bootstrap (state) and of the process path."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -372,6 +374,19 @@ def test_start_order_and_hand_over_policies_keep_every_bit(qp):
                 plan.bootstrap_into(bufs, probs, ref, 11, 0, method="mle", max_iter=1000, tol=1e-6)
             assert bool((bufs["dist"] == want_d).all()) and bool((bufs["iters"] == want_it).all()), (B, opts)
         assert int(want_it.max()) > 300
+
+
+def test_pauli2_scheduling_stress(qp):
+    """tools/stress_pauli2.py in short: 80 fused launches back to back with random batch sizes (around every policy
+    threshold), state ranks, tolerances, iteration caps and scheduling options; each equals the plain
+    thread-per-sample launch of the same inputs bit for bit (and none hangs: pytest-timeout is the guard)."""
+    import subprocess
+    import sys as _sys
+
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "stress_pauli2.py")
+    out = subprocess.run([_sys.executable, tool, "7", "80"], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "80 launches, 0 mismatches" in out.stdout, out.stdout[-2000:]
 
 
 @pytest.mark.parametrize("n", [1, 2, 31, 1000, 4097, 12500, 16384, 16385, 100000])
