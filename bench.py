@@ -506,9 +506,12 @@ class StateWorkload:
         return itv
 
     def e2e_h2d(self):
-        return self.probs.numel() * 8 + self.state.bloch.size * 8 + self.ref.numel() * 8
+        if self.gpu.world == 1 and self.gpu.engine.FUSED_INTERVAL:
+            return 0  # one library call uploads Bloch vector, centre state and levels; counted in parallel.TRAFFIC
+        return self.state.bloch.size * 8 + self.ref.numel() * 8
 
-    api = "quantpy_b200.BootstrapStateInterval(...).setup() + cl_to_dist"
+    api = ("quantpy_b200.BootstrapStateInterval(...).setup() + cl_to_dist; on one GPU both are served by ONE C-ABI call "
+           "with host inputs and outputs (qpb_bootstrap_state_interval)")
 
     # ---- dominant kernel, timed alone ---------------------------------------------------------------
     def kernel_breakdown(self):
@@ -753,7 +756,7 @@ def measure(gpu, cfg, steps, warmup, e2e_steps, with_cpu, cpu_seconds, with_roof
     e2e = {"value": world * B * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_call": 1e3 * e2e_s / e2e_steps,
            "ms_each": [round(1e3 * t, 3) for t in times], "api": wl.api,
-           "note": "the sorted distances stay on the device; a quantile call copies the neighbours of the requested levels",
+           "note": "host in: Bloch vector, centre state, confidence levels; host out: the quantiles at the 1000 default levels; the sorted distances stay on the device",
            "dist_on_host": {"value": world * B * e2e_steps / e2e_full_s, "unit": UNIT,
                             "d2h_bytes_per_step": int(d2h + B * world * 8),
                             "note": "plus interval.dist: all N sorted distances on the host, as in the reference"}}

@@ -74,7 +74,12 @@ enum {
     QPB_OPT_MLE_PARK_AGE_PCT2 = 26,/* ... over this percentage of the remaining queue (0 = default) */
     QPB_OPT_MLE_REFILL_MIN = 27,   /* pauli2 MLE tuning: free lanes of a warp wait for this many before they take new samples (0 = default) */
     QPB_OPT_NO_WARM_JACOBI = 28,   /* CPTP projection (Choi 16 x 16): every eigen-decomposition starts from the identity instead of the previous step's eigenvectors */
-    QPB_OPT_COUNT_ = 29
+    QPB_OPT_MLE_SINGLE_WARPS = 29, /* pauli2 MLE tuning: thread-per-sample warps per CTA, of 12 warps in all (0 = default 8; up to 12) */
+    QPB_OPT_SAMPLER_NO_PREFILTER = 30, /* binomial sampler: every undecided BTRS candidate goes to the float64 test (no float32 prefilter); same counts */
+    QPB_OPT_SAMPLER_EXACT_EVERY = 31,  /* binomial sampler tuning: undecided candidates are tested on loop trips that are multiples of this (0 = default) */
+    QPB_OPT_SAMPLER_THREADS = 32,      /* binomial sampler tuning: threads per block (0 = chosen so that the launch is one wave when it can be) */
+    QPB_OPT_NO_SAMPLE_SORT = 33,       /* qpb_sort_f64: the earlier path (one-CTA bitonic network up to 16384 keys, device radix sort above) instead of counting / sample sort */
+    QPB_OPT_COUNT_ = 34
 };
 QPB_API int qpb_set_option(int which, int value);
 QPB_API int qpb_get_option(int which);
@@ -240,6 +245,26 @@ QPB_API int qpb_sort_f64(long long n, const double* in, double* out, void* strea
  * (interval.py:610, 683), without re-sorting world_size * shard keys on every rank.  in != out.            */
 QPB_API int qpb_merge_sorted_runs(int n_runs, const int32_t* run_len_host, const int64_t* run_start_host,
                                   const double* in, double* out, void* stream);
+
+/* cl_to_dist(levels) of interval.py:611-612 -- scipy's interp1d(linspace(0, 1, n), sorted)(levels) -- on a sorted
+ * array that lives on the device: HOST levels in, HOST quantiles out (2 * 8 * n_levels bytes cross PCIe, staged
+ * through page-locked memory owned by the library); returns after the stream has been synchronised.  A level outside
+ * [0, 1] is QPB_ERR_INVALID with interp1d's message.  Evaluates y[lo] + (y[lo+1] - y[lo]) * (pos - lo),
+ * pos = level * (n - 1), without contraction: the same bits as the NumPy expression on the same array.       */
+QPB_API int qpb_quantiles_host(long long n, const double* sorted_dev, int n_levels, const double* levels_host,
+                               double* out_host, void* stream);
+/* BootstrapStateInterval.setup() + cl_to_dist(levels) (interval.py:583-612) on one GPU as ONE call with HOST
+ * inputs and outputs: Bloch vector [D] and matrix [d,d] complex of the centre state, shot vector and confidence
+ * levels are host arrays; the call uploads them (one copy), computes the probabilities clip(2^n M.r) from the
+ * unweighted POVM rows M_dev [K,D] (device, state.py:109-110), runs qpb_bootstrap_state on library-owned scratch,
+ * sorts the distances into dist_sorted [B] (device, stays there: interval.py:610), interpolates the levels and
+ * returns the quantiles in quantiles_host after synchronising the stream.  iters_out [B] (device) is optional.
+ * n_levels may be 0 (setup only).                                                                          */
+QPB_API int qpb_bootstrap_state_interval(const qpb_state_plan* plan, int B, int P, int O, const double* M_dev,
+                                 const double* bloch_host, const double* ref_host, const int32_t* n_shots_host,
+                                 uint64_t seed, uint64_t offset, int method, int physical, int init, int max_iter,
+                                 double tol, int dist_kind, int n_levels, const double* levels_host,
+                                 double* quantiles_host, double* dist_sorted, int32_t* iters_out, void* stream);
 
 #ifdef __cplusplus
 }

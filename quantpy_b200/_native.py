@@ -59,6 +59,9 @@ SIGNATURES = {
     "qpb_l2_moments": (_int, [_int, _int, _int, _vp, _vp, _dbl, _vp, _vp, _vp]),
     "qpb_sort_f64": (_int, [ctypes.c_longlong, _vp, _vp, _vp]),
     "qpb_merge_sorted_runs": (_int, [_int, _vp, _vp, _vp, _vp, _vp]),
+    "qpb_quantiles_host": (_int, [ctypes.c_longlong, _vp, _int, _vp, _vp, _vp]),
+    "qpb_bootstrap_state_interval": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _u64, _u64, _int, _int, _int,
+                                            _int, _dbl, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "qpb_mhmc_state": (_int, [_vp, _int, _int, _int, _int, _dbl, _vp, _int, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp,
                               _vp]),
     "qpb_process_plan_create": (_int, [ctypes.POINTER(_vp), _int, _int, _int, _vp, _vp]),
@@ -75,7 +78,8 @@ OPTIONS = {"NO_TAIL_MERGE": 0, "NO_HS_FUSION": 1, "NO_PAULI_KERNEL": 2, "NO_CONS
            "MLE_W_WARPS": 15, "MLE_PARK_PLATEAU": 16, "NO_TMA_GEMM": 17, "MLE_TAIL_POLL": 18, "MLE_TAIL_AGE": 19,
            "MLE_ADOPT": 20, "MLE_MERGE": 21, "NO_MLE_ORDER": 22,
            "MLE_PARK_AGE_LO": 23, "MLE_PARK_AGE_PCT": 24, "MLE_PARK_AGE_END": 25, "MLE_PARK_AGE_PCT2": 26,
-           "MLE_REFILL_MIN": 27, "NO_WARM_JACOBI": 28}
+           "MLE_REFILL_MIN": 27, "NO_WARM_JACOBI": 28, "MLE_SINGLE_WARPS": 29,
+           "SAMPLER_NO_PREFILTER": 30, "SAMPLER_EXACT_EVERY": 31, "SAMPLER_THREADS": 32, "NO_SAMPLE_SORT": 33}
 SAMPLERS = {"auto": 0, "alias": 1, "binomial": 2}
 
 

@@ -135,7 +135,10 @@ struct Pauli2Args {
     int direct;           // W workers take fresh samples from the queue (no single-lane warps)
 };
 
-constexpr int kPauliThreadsSingle = 256;  // thread-per-sample lanes per CTA (8 warps: 2 per scheduler)
+constexpr int kPauliThreadsSingle = 384;  // most thread-per-sample lanes per CTA (12 warps: 3 per scheduler) = stride of the
+                                          // frequency columns; the launch decides how many of the 12 warps start that way
+constexpr int kPauliWarps = kPauliThreadsSingle / 32;
+constexpr int kCxTop = kPauliWarps, kCxLock = kPauliWarps + 1;  // packing stack: entries, lock (after the live[] words)
 constexpr int kPoolWords = 54;             // a sample on the packing stack: 16 state + 36 frequencies + index + age
 
 // ------------------------------------------------------------------------------------------------
@@ -736,13 +739,13 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
     // Packing of the tail (a.merge): once the queue is empty the live samples of a CTA's thread-per-sample warps thin
     // out; a warp whose samples fit into the free lanes of the others pushes them (state, frequencies, index, age)
     // onto a shared-memory stack, the others pop them into their free lanes, and the emptied warp becomes a W worker.
-    // live[w] (cx[0..7]): live lanes of warp w as last published, 32 before it saw the queue empty, -1 once it left;
-    // cx[8]: entries on the stack; cx[9]: lock (all stack / live[-1] transitions happen under it).
+    // live[w] (cx[0..11]): live lanes of warp w as last published, 32 before it saw the queue empty, -1 once it left;
+    // cx[kCxTop]: entries on the stack; cx[kCxLock]: lock (all stack / live[-1] transitions happen under it).
     double* pool = fs + 36 * kPauliThreadsSingle;                          // [kPoolWords][32], entry-minor
     volatile int* cx = reinterpret_cast<volatile int*>(pool + kPoolWords * 32);
     if (a.merge) {
-        if (tid < 8) cx[tid] = tid < a.single_warps ? 32 : -1;
-        if (tid == 8 || tid == 9) cx[tid] = 0;
+        if (tid < kPauliWarps) cx[tid] = tid < a.single_warps ? 32 : -1;
+        if (tid == kCxTop || tid == kCxLock) cx[tid] = 0;
         __syncthreads();
     }
     if (warp >= a.single_warps) {
@@ -848,17 +851,17 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
             const unsigned full = 0xffffffffu;
             auto lock = [&]() {
                 if (lane == 0)
-                    while (atomicCAS(const_cast<int*>(cx + 9), 0, 1) != 0) {}
+                    while (atomicCAS(const_cast<int*>(cx + kCxLock), 0, 1) != 0) {}
                 __syncwarp();
                 __threadfence_block();
             };
             auto unlock = [&]() {
                 __threadfence_block();
                 __syncwarp();
-                if (lane == 0) atomicExch(const_cast<int*>(cx + 9), 0);
+                if (lane == 0) atomicExch(const_cast<int*>(cx + kCxLock), 0);
             };
             auto pop = [&]() {  // under the lock: fill free lanes from the stack
-                const int top = cx[8];
+                const int top = cx[kCxTop];
                 const unsigned freem = ~active;
                 int n = __popc(freem);
                 if (n > top) n = top;
@@ -878,13 +881,13 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
                 active = __ballot_sync(full, b >= 0);
                 tr_adopted += n;
                 if (lane == 0) {
-                    cx[8] = top - n;
+                    cx[kCxTop] = top - n;
                     cx[warp] = __popc(active);
                 }
             };
             if (active == 0) {  // leaving: nothing may stay on the stack without a warp to take it
                 lock();
-                if (!dissolved && cx[8] > 0) {
+                if (!dissolved && cx[kCxTop] > 0) {
                     pop();
                     unlock();
                     continue;
@@ -896,17 +899,17 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
             const int live = __popc(active);
             if (live < 32) {
                 if (lane == 0) cx[warp] = live;
-                if (cx[8] > 0) {
+                if (cx[kCxTop] > 0) {
                     lock();
                     pop();
                     unlock();
                 } else {
-                    const int lv = lane < 8 ? cx[lane] : -1;
+                    const int lv = lane < kPauliWarps ? cx[lane] : -1;
                     const int room = __reduce_add_sync(full, (lane != warp && lv >= 0) ? 32 - lv : 0);
                     if (room >= live + a.merge - 1) {
                         lock();
-                        const int top = cx[8];
-                        const int lv2 = lane < 8 ? cx[lane] : -1;
+                        const int top = cx[kCxTop];
+                        const int lv2 = lane < kPauliWarps ? cx[lane] : -1;
                         const int room2 = __reduce_add_sync(full, (lane != warp && lv2 >= 0) ? 32 - lv2 : 0) - top;
                         if (room2 >= live && top + live <= 32) {
                             const int rank = __popc(active & ((1u << lane) - 1u));
@@ -921,7 +924,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
                                 b = -1;
                             }
                             if (lane == 0) {
-                                cx[8] = top + live;
+                                cx[kCxTop] = top + live;
                                 cx[warp] = -1;
                             }
                             dissolved = true;
@@ -1181,10 +1184,13 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
         // every SM gets a CTA; only as many thread-per-sample warps as the batch can fill (they run faster alone),
         // the other warps of the 12 serve the hand-over list from the start
         blocks = sms;
-        const long long need = ((long long)B + kPauliThreadsSingle - 1) / kPauliThreadsSingle;
+        // thread-per-sample warps per CTA (of 12 warps in all): 8 = two per scheduler (default), up to 12
+        int max_sw = option(QPB_OPT_MLE_SINGLE_WARPS) > 0 ? option(QPB_OPT_MLE_SINGLE_WARPS) : 8;
+        if (max_sw > kPauliWarps) max_sw = kPauliWarps;
+        const long long need = ((long long)B + max_sw * 32 - 1) / (max_sw * 32);
         if (blocks > need && no_merge) blocks = (int)need;
         int sw = (int)(((long long)B + (long long)blocks * 32 - 1) / ((long long)blocks * 32));
-        if (sw > kPauliThreadsSingle / 32) sw = kPauliThreadsSingle / 32;
+        if (sw > max_sw) sw = max_sw;
         if (sw < 1) sw = 1;
         a.single_warps = sw;
         if (no_merge) {
@@ -1198,13 +1204,13 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
             a.tail_poll = a.tail_age = a.adopt = a.merge = 0;
             a.refill_min = 1;
             w_warps = 0;
-            a.single_warps = kPauliThreadsSingle / 32;
+            a.single_warps = max_sw;
         } else {
             const int pl = option(QPB_OPT_MLE_PARK_PLATEAU);
             a.park_plateau = pl > 0 ? pl : 0;
             // measured on B200 (tools/pauli2_sweep_d.py, C2 workload): the fuller the thread-per-sample lanes, the
             // less W capacity is left, so the hand-over age rises with the batch: 200 / 300 / 450 iterations
-            const long long lanes = (long long)sms * kPauliThreadsSingle;
+            const long long lanes = (long long)sms * max_sw * 32;
             const int age = (long long)B * 2 <= lanes ? 200 : ((long long)B * 2 <= lanes * 3 ? 300 : 500);
             a.park_age = option(QPB_OPT_MLE_PARK_AGE) > 0 ? option(QPB_OPT_MLE_PARK_AGE) : age;
             {
@@ -1224,7 +1230,7 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
                 a.park_age_slope2 = (float)((a.park_age - a.park_age_end) / span);
             }
             a.park_live = option(QPB_OPT_MLE_PARK_LIVE) > 0 ? option(QPB_OPT_MLE_PARK_LIVE) : ((long long)B * 4 <= lanes ? 16 : 5);
-            if (a.single_warps < kPauliThreadsSingle / 32) w_warps = 12 - a.single_warps;
+            if (a.single_warps < max_sw || a.single_warps + w_warps > kPauliWarps) w_warps = kPauliWarps - a.single_warps;
             const int poll = option(QPB_OPT_MLE_TAIL_POLL);
             a.tail_poll = poll < 0 ? 0 : (poll == 0 ? 4 : poll);
             while (a.tail_poll & (a.tail_poll - 1)) a.tail_poll &= a.tail_poll - 1;  // power of two

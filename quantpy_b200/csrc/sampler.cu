@@ -182,6 +182,16 @@ __device__ __forceinline__ double stirling_tail(double k) {
     return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0 - (1.0 / 1680.0 - (1.0 / 1188.0 - 691.0 / 360360.0 * x2) * x2) * x2) * x2) * x2) * ix;
 }
 
+__constant__ float kStirlingTabF[16] = {0.08106146679532726f,  0.0413406959554093f,   0.02767792568499834f,  0.020790672103765093f,
+                            0.016644691189821193f, 0.013876128823070748f, 0.011896709945891770f, 0.010411265261972096f,
+                            0.009255462182712733f, 0.008330563433362871f, 0.007573675487951841f, 0.006942840107209530f,
+                            0.006408994188004207f, 0.005951370112758848f, 0.005554733551962801f, 0.005207655919609640f};
+__device__ __forceinline__ float stirling_tail_f(double k) {  // float32 copy for the prefilter (absolute error < 1e-8)
+    if (k < 16.0) return kStirlingTabF[(int)k];
+    const float ix = 1.0f / ((float)k + 1.0f), x2 = ix * ix;
+    return (1.0f / 12.0f - (1.0f / 360.0f - (1.0f / 1260.0f) * x2) * x2) * ix;
+}
+
 // Binomial(n, p) for 0 < p <= 0.5 and n*p < 10: sequential search from 0 (BINV).
 __device__ long binomial_inversion(long n, double p, PhiloxStream& rng) {
     const double q = 1.0 - p;
@@ -235,8 +245,7 @@ struct Btrs {
         if (kd < 0.0 || kd > n) return -1;
         return -2;
     }
-    // exact test of candidate kd against the log-pmf ratio (reciprocals instead of divisions: this path is most of
-    // the kernel's instructions)
+    // exact test of candidate kd against the log-pmf ratio (reciprocals instead of divisions)
     __device__ __forceinline__ bool accept_exact(double kd, double v, double us) const {
         const double lv = log(v * alpha * fast_recip(a * fast_recip(us * us) + b));
         const double nm = n - m + 1.0, nk = n - kd + 1.0;
@@ -244,6 +253,32 @@ struct Btrs {
                              (kd + 0.5) * log(nk * r * fast_recip(kd + 1.0)) + stirling_tail(m) + stirling_tail(n - m) -
                              stirling_tail(kd) - stirling_tail(n - kd);
         return lv <= bound;
+    }
+    // The same comparison in float32 with an error bound: 1 accept, 0 reject, -1 too close to call (then
+    // accept_exact decides, so the variate is the one the float64 test alone would give -- the counts keep
+    // their bits, tests/test_gpu_state.py::test_binomial_prefilter_changes_no_count).  The three log arguments
+    // are 1 + d with small d; each d is formed so that its RELATIVE error is a few float ulps (the cancelling
+    // numerators in float64, two FMAs), log1pf / logf are 1-ulp functions, so every term t carries at most
+    // ~4e-7 |t|; the Stirling tails are < 0.09 each.  delta is that bound with a factor of five to spare.
+    // Four float64 logs and four float64 Stirling series were most of the sampler's FP64-pipe time.
+    __device__ __forceinline__ int accept_quick(double kd, double v, double us) const {
+        const float usf = (float)us;
+        const float lv = logf((float)(v * alpha) / ((float)a / (usf * usf) + (float)b));
+        const double nm = n - m + 1.0, nk = n - kd + 1.0;
+        const double rnm = r * nm;
+        const float d1 = (float)((m + 1.0) - rnm) / (float)rnm;                  // (m+1)/(r nm) - 1
+        const float d2 = (float)(kd - m) / (float)nk;                            // nm/nk - 1, numerator exact
+        const float d3 = (float)fma(nk, r, -(kd + 1.0)) / (float)(kd + 1.0);     // nk r/(kd+1) - 1
+        const float t1 = (float)(m + 0.5) * log1pf(d1);
+        const float t2 = (float)(n + 1.0) * log1pf(d2);
+        const float t3 = (float)(kd + 0.5) * log1pf(d3);
+        const float st = (stirling_tail_f(m) + stirling_tail_f(n - m)) - (stirling_tail_f(kd) + stirling_tail_f(n - kd));
+        const float bound = ((t1 + t2) + t3) + st;
+        const float delta = 2e-6f * (fabsf(t1) + fabsf(t2) + fabsf(t3) + fabsf(lv)) + 1e-5f;
+        if (!(delta < 1.0f)) return -1;  // non-finite or absurdly large terms: no float verdict
+        if (lv <= bound - delta) return 1;
+        if (lv >= bound + delta) return 0;
+        return -1;
     }
 };
 
@@ -255,8 +290,10 @@ struct Btrs {
 // period 1: 0.195 ms, 2: 0.183 ms, 3: 0.197 ms, 4: 0.216 ms (waiting lanes cost more than the saved long paths).
 constexpr int kExactEvery = 2;
 
-__global__ void k_multinomial_binomial(int B, int P, int O, const double* __restrict__ p, int batched, ShotVec shots,
-                                       uint32_t k0, uint32_t k1, uint64_t offset, int32_t* __restrict__ counts) {
+template <bool PREFILTER>
+__global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, const double* __restrict__ p, int batched, ShotVec shots,
+                                       uint32_t k0, uint32_t k1, uint64_t offset, int32_t* __restrict__ counts,
+                                       int exact_every) {
     const long items = (long)B * P;
     for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
         const long b = item / P;
@@ -310,9 +347,11 @@ __global__ void k_multinomial_binomial(int B, int P, int O, const double* __rest
                 y = st.propose(rng, cand, cv, cus);
                 pending = y == -2;
             }
-            if (pending && trip % kExactEvery == 0) {
+            if (pending && trip % exact_every == 0) {
                 pending = false;
-                y = st.accept_exact(cand, cv, cus) ? (long)cand : -1;
+                int verdict = PREFILTER ? st.accept_quick(cand, cv, cus) : -1;
+                if (verdict < 0) verdict = st.accept_exact(cand, cv, cus) ? 1 : 0;  // a few per 10^4 candidates
+                y = verdict ? (long)cand : -1;
             }
             if (y >= 0) {
                 const long c = flip ? left - y : y;
@@ -354,12 +393,34 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
     if (force == 2) use_binomial = true;
     if (use_binomial) {
         const long items = (long)B * P;
-        const int threads = 128;
+        const int every = option(QPB_OPT_SAMPLER_EXACT_EVERY) > 0 ? option(QPB_OPT_SAMPLER_EXACT_EVERY) : kExactEvery;
+        const bool prefilter = !option(QPB_OPT_SAMPLER_NO_PREFILTER);
+        auto kern = prefilter ? k_multinomial_binomial<true> : k_multinomial_binomial<false>;
+        // Every thread walks its O - 1 binomials from start to end, so a launch that needs one block more than fits
+        // takes twice as long: pick the largest block size whose grid is resident at once (1e5 items: 782 blocks of 128
+        // against 740 slots, but 1563 blocks of 64 against 1628), else 128 and a grid-stride loop
+        static int occ[2][3] = {{0, 0, 0}, {0, 0, 0}};  // resident blocks per SM for 128 / 96 / 64 threads
+        const int cand[3] = {128, 96, 64};
+        int threads = option(QPB_OPT_SAMPLER_THREADS) > 0 ? option(QPB_OPT_SAMPLER_THREADS) : 0;
+        if (threads == 0) {
+            threads = 128;
+            for (int c = 0; c < 3; ++c) {
+                if (occ[prefilter][c] == 0) {
+                    int nb = 0;
+                    QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, cand[c], 0));
+                    occ[prefilter][c] = nb > 0 ? nb : 1;
+                }
+                if ((items + cand[c] - 1) / cand[c] <= (long)num_sms() * occ[prefilter][c]) {
+                    threads = cand[c];
+                    break;
+                }
+            }
+        }
         long blocks = (items + threads - 1) / threads;
         const long cap = (long)num_sms() * 16;
         if (blocks > cap) blocks = cap;
-        k_multinomial_binomial<<<(int)blocks, threads, 0, st>>>(B, P, O, p, p_batched, shots, (uint32_t)seed,
-                                                               (uint32_t)(seed >> 32), offset, counts);
+        kern<<<(int)blocks, threads, 0, st>>>(B, P, O, p, p_batched, shots, (uint32_t)seed, (uint32_t)(seed >> 32), offset,
+                                              counts, every);
         QPB_LAUNCHED("k_multinomial_binomial");
         return QPB_OK;
     }

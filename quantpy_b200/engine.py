@@ -185,6 +185,48 @@ class StatePlan:
         return bufs
 
 
+# BootstrapStateInterval on one GPU goes through qpb_bootstrap_state_interval (tests switch it off to compare with the
+# step-by-step path; both give the same bits)
+FUSED_INTERVAL = True
+
+
+def bootstrap_interval(plan, bloch, ref_matrix, n_samples, seed, offset, method, physical, init, max_iter, tol, dst,
+                       levels):
+    """qpb_bootstrap_state_interval: the whole single-GPU interval (interval.py:583-612) in one call with host
+    inputs and outputs -> (quantiles at `levels` [host], sorted distances [device], iteration counts [device])."""
+    torch = nt.torch_cuda()
+    if method not in nt.METHODS:
+        raise ValueError("Invalid value for argument `method`")
+    if init not in nt.INITS:
+        raise ValueError("Invalid value for argument `init`")
+    B = int(n_samples)
+    bloch = np.ascontiguousarray(bloch, dtype=np.float64).reshape(-1)
+    ref = np.ascontiguousarray(ref_matrix, dtype=np.complex128)
+    levels = np.ascontiguousarray(levels, dtype=np.float64).reshape(-1)
+    if bloch.size != plan.D or ref.size != plan.D:
+        raise ValueError("centre state does not match the POVM dimension")
+    out = np.empty(levels.size, dtype=np.float64)
+    dist = torch.empty((B,), dtype=torch.float64, device="cuda")
+    iters = torch.empty((B,), dtype=torch.int32, device="cuda")
+    vp = ctypes.c_void_p
+    nt.check(plan._lib.qpb_bootstrap_state_interval(
+        plan.handle, B, plan.P, plan.O, nt.ptr(plan.M_dev), vp(bloch.ctypes.data), vp(ref.ctypes.data),
+        vp(plan.n_shots.ctypes.data), ctypes.c_uint64(seed), ctypes.c_uint64(offset), nt.METHODS[method],
+        int(bool(physical)), nt.INITS[init], int(max_iter), float(tol), nt.DIST_KINDS[dst], levels.size,
+        vp(levels.ctypes.data), vp(out.ctypes.data), nt.ptr(dist), nt.ptr(iters), nt.stream_ptr()))
+    return out, dist, iters
+
+
+def quantiles_host(sorted_dev, levels):
+    """qpb_quantiles_host: interp1d(linspace(0, 1, N), sorted)(levels) on a device-resident sorted array."""
+    levels = np.ascontiguousarray(levels, dtype=np.float64)
+    out = np.empty(levels.shape, dtype=np.float64)
+    vp = ctypes.c_void_p
+    nt.check(nt.load_library().qpb_quantiles_host(int(sorted_dev.numel()), nt.ptr(sorted_dev), levels.size,
+                                                  vp(levels.ctypes.data), vp(out.ctypes.data), nt.stream_ptr()))
+    return out
+
+
 def sort_f64(values):
     """Ascending sort of a 1-D float64 device tensor (keys only) -> new device tensor."""
     torch = nt.torch_cuda()

@@ -142,8 +142,9 @@ class QuantileFunction:
     reference builds with scipy.interpolate.interp1d(conf_levels, dist) (quantpy/tomography/interval.py:610-612).
     Same call semantics (vectorised, ValueError outside [0, 1]) and the same `.x` / `.y` attributes.
 
-    The sorted values may stay ON THE DEVICE: a call then fetches only the two neighbours of every requested
-    level (a few KB), and nothing of size N crosses PCIe unless `.y` (or the interval's `.dist`) is asked for."""
+    The sorted values may stay ON THE DEVICE: a call then sends the requested levels and receives their quantiles
+    (a few KB, qpb_quantiles_host), and nothing of size N crosses PCIe unless `.y` (or the interval's `.dist`) is
+    asked for."""
 
     def __init__(self, sorted_values):
         self._dev = None
@@ -157,6 +158,7 @@ class QuantileFunction:
             self._y = np.asarray(sorted_values, dtype=np.float64)
             self._n = len(self._y)
         self._x = None
+        self._primed = None
 
     @property
     def y(self):
@@ -177,29 +179,28 @@ class QuantileFunction:
         if np.any(levels > 1):
             raise ValueError("A value in x_new is above the interpolation range.")
         n = self._n
+        if self._y is None:
+            # device-resident: the levels go up, the quantiles come back (qpb_quantiles_host evaluates the expression
+            # below in the same IEEE operations); a call with the levels the interval was set up with is answered
+            # from what that call already brought back
+            if self._primed is not None and self._primed[0].shape == levels.shape and np.array_equal(self._primed[0], levels):
+                return self._primed[1].copy()
+            from . import engine
+
+            TRAFFIC["h2d"] += levels.size * 8
+            TRAFFIC["d2h"] += levels.size * 8
+            return engine.quantiles_host(self._dev, levels)
         if n == 1:
-            return np.full(levels.shape, self.y[0])
+            return np.full(levels.shape, self._y[0])
         pos = levels * (n - 1)
         lo = np.minimum(np.floor(pos).astype(np.int64), n - 2)
         frac = pos - lo
-        if self._y is None:
-            import torch
-
-            m = 2 * lo.size
-            stage = _pinned(torch.int64, m)  # both copies go through page-locked staging: no pageable round trips
-            stage.numpy()[: lo.size] = lo.reshape(-1)
-            stage.numpy()[lo.size:] = lo.reshape(-1) + 1
-            idx = stage.to(self._dev.device, non_blocking=True)
-            out = _pinned(torch.float64, m)
-            out.copy_(self._dev[idx], non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            pair = out.numpy().copy()
-            TRAFFIC["h2d"] += m * 8
-            TRAFFIC["d2h"] += m * 8
-            y_lo, y_hi = pair[: lo.size].reshape(lo.shape), pair[lo.size:].reshape(lo.shape)
-        else:
-            y_lo, y_hi = self._y[lo], self._y[lo + 1]
+        y_lo, y_hi = self._y[lo], self._y[lo + 1]
         return y_lo + (y_hi - y_lo) * frac
+
+    def prime(self, levels, values):
+        """Remember the quantiles a fused set-up call already returned for `levels`."""
+        self._primed = (np.array(levels, dtype=np.float64), np.array(values, dtype=np.float64))
 
 
 def quantile_function(dist_values, presorted=False):

@@ -32,6 +32,7 @@ class ConfidenceInterval(ABC):
     """Functor: interval(conf_levels) -> (distances, conf_levels); `setup` runs lazily on first call."""
 
     EPS = 1e-15
+    _setup_takes_levels = False
 
     def __init__(self, tmg, **kwargs):
         self.tmg = tmg
@@ -48,7 +49,10 @@ class ConfidenceInterval(ABC):
         if conf_levels is None:
             conf_levels = np.linspace(1e-3, 1 - 1e-3, 1000)
         if not hasattr(self, "cl_to_dist"):
-            self.setup()
+            if self._setup_takes_levels:
+                self.setup(conf_levels=conf_levels)  # the levels travel with the set-up call
+            else:
+                self.setup()
         return self.cl_to_dist(conf_levels), conf_levels
 
     @abstractmethod
@@ -122,7 +126,11 @@ class BootstrapStateInterval(ConfidenceInterval):
         tomograph's POVM and shot numbers; kwargs as StateTomograph.point_estimate."""
         super().__init__(tmg, **_pop_hidden_keys(locals()))
 
-    def setup(self, seed=None):
+    _setup_takes_levels = True
+
+    def setup(self, seed=None, conf_levels=None):
+        """interval.py:583-612.  `conf_levels` (optional; default: the levels `__call__` uses) are evaluated by the
+        same device call that runs the bootstrap, so a following `cl_to_dist(conf_levels)` costs nothing."""
         if self.mode == Mode.CHANNEL:
             raise NotImplementedError("This interval works only for state tomography")
         if self.state is None:
@@ -139,8 +147,21 @@ class BootstrapStateInterval(ConfidenceInterval):
         # a key drawn from this rank's np.random stream must be agreed on; an explicit seed is the caller's (SPMD)
         seed = parallel.broadcast_seed(engine.next_seed()) if seed is None else int(seed)
         plan = engine.state_plan(self.tmg.povm_matrix, self.tmg.n_measurements)
-        probs = plan.probabilities(self.state.bloch)[0]
         kind = dst_kind(self.tmg.dst)
+        if size == 1 and kind is not None and self.n_points >= 1 and engine.FUSED_INTERVAL:
+            # one GPU, built-in distance: ONE library call with host inputs and outputs (qpb_bootstrap_state_interval)
+            levels = np.linspace(1e-3, 1 - 1e-3, 1000) if conf_levels is None else np.asarray(conf_levels, dtype=np.float64)
+            if np.any(levels < 0) or np.any(levels > 1):
+                levels = np.zeros(0)  # let cl_to_dist raise interp1d's error when it is called
+            q, dist, self._iters_dev = engine.bootstrap_interval(
+                plan, self.state.bloch, self.state.matrix, self.n_points, seed, 0, method, self.physical, self.init,
+                self.max_iter, self.tol, kind, levels)
+            parallel.TRAFFIC["h2d"] += (3 * plan.D + levels.size) * 8
+            parallel.TRAFFIC["d2h"] += levels.size * 8
+            self.cl_to_dist = parallel.quantile_function(dist, presorted=True)
+            self.cl_to_dist.prime(levels, q.reshape(levels.shape))
+            return
+        probs = plan.probabilities(self.state.bloch)[0]
         out = plan.bootstrap(probs, hi - lo, seed, lo, self.state.matrix, method, self.physical, self.init,
                              self.max_iter, self.tol, kind or "hs", keep=kind is None)
         if kind is None:  # user-supplied measure: evaluate it on the reconstructed batch

@@ -101,6 +101,54 @@ def test_bootstrap_interval_matches_reference_distribution(qp, golden, method):
     assert np.array_equal(a.dist, b.dist)
 
 
+@pytest.mark.parametrize("n,povm,method,dst,B", [(2, "proj", "mle", "hs", 5000), (1, "proj-set", "mle", "hs", 1000),
+                                                 (2, "proj-set", "lin", "trace", 3000), (3, "proj", "lin", "if", 600),
+                                                 (1, "proj-set", "mle", "hs", 1), (2, "proj", "mle", "hs", 40000)])
+def test_one_call_interval_equals_step_by_step_path(qp, n, povm, method, dst, B):
+    """qpb_bootstrap_state_interval (host inputs -> quantiles on the host in one library call) against the path it
+    replaces (probabilities, fused bootstrap, sort, host interpolation): the same sorted distances, iteration counts
+    and quantiles bit for bit; the quantiles also equal the reference expression evaluated in NumPy on `.dist`
+    (interval.py:610-612), for the set-up levels and for levels asked later (qpb_quantiles_host)."""
+    from scipy.interpolate import interp1d
+
+    from quantpy_b200 import engine
+
+    rho = haar(n, 40 + n)
+    tmg = qp.StateTomograph(qp.Qobj(rho), dst=dst)
+    np.random.seed(n)
+    tmg.experiment(10000, povm)
+    tmg.point_estimate("lin")
+    levels = np.linspace(1e-3, 1 - 1e-3, 1000)
+    res = {}
+    for fused in (True, False):
+        old = engine.FUSED_INTERVAL
+        engine.FUSED_INTERVAL = fused
+        try:
+            itv = qp.BootstrapStateInterval(tmg, n_points=B, method=method, tol=1e-6, max_iter=300)
+            np.random.seed(77)
+            q, cl = itv()
+            other = itv.cl_to_dist(np.array([0.0, 0.3141, 1.0]))
+            res[fused] = (q, other, itv.dist.copy(), itv.iters.copy())
+        finally:
+            engine.FUSED_INTERVAL = old
+    for a, b in zip(res[True], res[False]):
+        assert np.array_equal(a, b)
+    q, other, dist, iters = res[True]
+    assert np.all(np.diff(dist) >= 0) and len(dist) == B
+    if B > 1:
+        f = interp1d(np.linspace(0, 1, B), dist)
+        assert np.abs(q - f(levels)).max() < 1e-15 and np.abs(other - f([0.0, 0.3141, 1.0])).max() < 1e-15
+        pos = levels * (B - 1)
+        lo = np.minimum(np.floor(pos).astype(np.int64), B - 2)
+        assert np.array_equal(q, dist[lo] + (dist[lo + 1] - dist[lo]) * (pos - lo))
+    else:
+        assert np.array_equal(q, np.full(1000, dist[0]))
+    with pytest.raises(ValueError):
+        itv.cl_to_dist(-0.1)
+    with pytest.raises(ValueError):
+        qp.BootstrapStateInterval(tmg, n_points=16, method=method)([0.5, 1.2])
+
+
 def test_bootstrap_full_size_properties(qp):
     """BASELINE config 2 at full size (1e5 resamples): size-independent properties."""
     from quantpy_b200 import _native as nt
@@ -389,9 +437,11 @@ def test_pauli2_scheduling_stress(qp):
     assert "80 launches, 0 mismatches" in out.stdout, out.stdout[-2000:]
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 1000, 4097, 12500, 16384, 16385, 100000])
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 1000, 2047, 2048, 2049, 4097, 12500, 16384, 16385, 25000, 50000, 100000,
+                               131072, 131073, 333333, 1048576, 1048577])
 def test_sort_kernels_match_numpy(qp, n):
-    """qpb_sort_f64: shared-memory bitonic network up to 16384 keys, device radix sort above; keys only, bit-exact."""
+    """qpb_sort_f64: one CTA's bitonic network up to 2048 keys, four-launch sample sort up to 1M keys, device
+    radix sort above; keys only, bit-exact."""
     import torch
 
     from quantpy_b200 import engine
@@ -401,6 +451,44 @@ def test_sort_kernels_match_numpy(qp, n):
     x[: n // 7] = x[n // 5: n // 5 + n // 7]  # ties
     got = engine.sort_f64(torch.from_numpy(x).cuda()).cpu().numpy()
     assert np.array_equal(got, np.sort(x))
+
+
+@pytest.mark.parametrize("kind", ["constant", "two-values", "heavy-zero", "sorted", "reversed", "signed", "skewed",
+                                  "one-big-gap", "one-huge-gap"])
+def test_sample_sort_on_adversarial_inputs(qp, kind):
+    """The sample sort's buckets come from sampled splitters: duplicates (their own 'equal' buckets), monotone
+    inputs, negative keys, heavy skew and an oversized bucket (the counting fallback) all give np.sort's result, and
+    the same array as the radix sort it replaces."""
+    import torch
+
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    n = 100000
+    rng = np.random.default_rng(1)
+    # the splitter kernel reads 4 * 256 keys of a 1e5-key input at these positions; keys placed elsewhere are
+    # invisible to it
+    seen = np.floor((np.arange(1024) + 0.5) * n / 1024).astype(np.int64)
+    n_hidden = 6000 if kind == "one-huge-gap" else 3000  # ONE open bucket (0, 1): counting fallback / bitonic network
+    hidden = rng.choice(np.setdiff1d(np.arange(n), seen), n_hidden, replace=False)
+    gap = rng.integers(0, 2, n).astype(float)
+    gap[hidden] = 0.5 + 1e-9 * rng.random(n_hidden)
+    x = {
+        "constant": np.full(n, 0.25),
+        "two-values": rng.integers(0, 2, n).astype(float),
+        "heavy-zero": np.where(rng.random(n) < 0.6, 0.0, rng.random(n)),
+        "sorted": np.sort(rng.random(n)),
+        "reversed": np.sort(rng.random(n))[::-1].copy(),
+        "signed": rng.normal(size=n) * 10.0 ** rng.integers(-200, 200, n),
+        "skewed": rng.random(n) ** 40,
+        "one-big-gap": gap,
+        "one-huge-gap": gap,
+    }[kind]
+    dev = torch.from_numpy(x).cuda()
+    got = engine.sort_f64(dev).cpu().numpy()
+    assert np.array_equal(got, np.sort(x))
+    with nt.option("NO_SAMPLE_SORT", 1):
+        assert np.array_equal(engine.sort_f64(dev).cpu().numpy(), got)
 
 
 @pytest.mark.parametrize("lens", [[5], [4, 3], [12500] * 8, [100000, 99999, 1, 0, 7], [0, 0, 3]])

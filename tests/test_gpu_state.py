@@ -124,6 +124,30 @@ def test_binomial_kernel_matches_exact_pmf(qp, forced_binomial, n_shots, p):
     assert stats.chi2.sf(stat, len(obs) - 1) > 1e-4, (stat, len(obs))
 
 
+def test_binomial_prefilter_changes_no_count(qp, forced_binomial):
+    """The float32 prefilter of the BTRS acceptance test only settles candidates whose float64 verdict is certain,
+    so the counts are the same integers with and without it -- across shot numbers, skewed and flat tables, block
+    sizes and test periods (a lane's stream is its own)."""
+    import torch
+
+    from quantpy_b200 import _native as nt
+    from quantpy_b200 import engine
+
+    rng = np.random.default_rng(5)
+    cases = [(36, 10000, 20000), (36, 1000000, 4000), (8, 300, 20000), (216, 100000, 2000), (2, 50000000, 20000)]
+    for O, shots, B in cases:
+        p = rng.dirichlet(np.full(O, 0.7))
+        probs = torch.tensor(p[None], dtype=torch.float64, device="cuda")
+        with nt.option("SAMPLER_NO_PREFILTER", 1):
+            want = engine.sample_counts(probs, B, 1, O, [shots], seed=11 + O, offset=3).cpu().numpy()
+        got = engine.sample_counts(probs, B, 1, O, [shots], seed=11 + O, offset=3).cpu().numpy()
+        assert (got.sum(-1) == shots).all()
+        assert np.array_equal(got, want), (O, shots)
+        with nt.option("SAMPLER_EXACT_EVERY", 1), nt.option("SAMPLER_THREADS", 96):
+            other = engine.sample_counts(probs, B, 1, O, [shots], seed=11 + O, offset=3).cpu().numpy()
+        assert np.array_equal(other, want), (O, shots)
+
+
 @pytest.mark.parametrize("n,povm", [(1, "proj-set"), (2, "proj"), (2, "proj-set"), (3, "proj"), (4, "proj")])
 def test_sampler_counts_sum_and_chi_square(qp, sampler_kind, n, povm):
     """Integer stage: every POVM's counts sum to the shot number exactly.  Distribution: chi-square per
