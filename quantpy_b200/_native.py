@@ -79,7 +79,8 @@ OPTIONS = {"NO_TAIL_MERGE": 0, "NO_HS_FUSION": 1, "NO_PAULI_KERNEL": 2, "NO_CONS
            "MLE_ADOPT": 20, "MLE_MERGE": 21, "NO_MLE_ORDER": 22,
            "MLE_PARK_AGE_LO": 23, "MLE_PARK_AGE_PCT": 24, "MLE_PARK_AGE_END": 25, "MLE_PARK_AGE_PCT2": 26,
            "MLE_REFILL_MIN": 27, "NO_WARM_JACOBI": 28, "MLE_SINGLE_WARPS": 29,
-           "SAMPLER_NO_PREFILTER": 30, "SAMPLER_EXACT_EVERY": 31, "SAMPLER_THREADS": 32, "NO_SAMPLE_SORT": 33}
+           "SAMPLER_NO_PREFILTER": 30, "SAMPLER_EXACT_EVERY": 31, "SAMPLER_THREADS": 32, "NO_SAMPLE_SORT": 33,
+           "SAMPLER_LANES": 34}
 SAMPLERS = {"auto": 0, "alias": 1, "binomial": 2}
 
 

@@ -95,7 +95,8 @@ static const char* const kOptionEnv[QPB_OPT_COUNT_] = {
     "QPB_MLE_TAIL_POLL", "QPB_MLE_TAIL_AGE", "QPB_MLE_ADOPT", "QPB_MLE_MERGE", "QPB_NO_MLE_ORDER",
     "QPB_MLE_PARK_AGE_LO", "QPB_MLE_PARK_AGE_PCT", "QPB_MLE_PARK_AGE_END", "QPB_MLE_PARK_AGE_PCT2",
     "QPB_MLE_REFILL_MIN", "QPB_NO_WARM_JACOBI", "QPB_MLE_SINGLE_WARPS",
-    "QPB_SAMPLER_NO_PREFILTER", "QPB_SAMPLER_EXACT_EVERY", "QPB_SAMPLER_THREADS", "QPB_NO_SAMPLE_SORT"};
+    "QPB_SAMPLER_NO_PREFILTER", "QPB_SAMPLER_EXACT_EVERY", "QPB_SAMPLER_THREADS", "QPB_NO_SAMPLE_SORT",
+    "QPB_SAMPLER_LANES"};
 static const bool g_options_loaded = [] {
     for (int i = 0; i < QPB_OPT_COUNT_; ++i) {
         const char* e = kOptionEnv[i] ? getenv(kOptionEnv[i]) : nullptr;

@@ -290,23 +290,101 @@ struct Btrs {
 // period 1: 0.195 ms, 2: 0.183 ms, 3: 0.197 ms, 4: 0.216 ms (waiting lanes cost more than the saved long paths).
 constexpr int kExactEvery = 2;
 
+// One Binomial(n, p) variate, blocking (the group splits of the lanes-per-item decomposition below).
 template <bool PREFILTER>
+__device__ long binomial_variate(long n, double p, PhiloxStream& rng) {
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    const bool flip = p > 0.5;
+    const double r = flip ? 1.0 - p : p;
+    if (!(r > 0.0)) return flip ? n : 0;
+    long y;
+    if ((double)n * r < 10.0) {
+        y = binomial_inversion(n, r, rng);
+    } else {
+        Btrs st;
+        st.setup(n, r);
+        for (;;) {
+            double kd, v, us;
+            y = st.propose(rng, kd, v, us);
+            if (y == -2) {
+                int verdict = PREFILTER ? st.accept_quick(kd, v, us) : -1;
+                if (verdict < 0) verdict = st.accept_exact(kd, v, us) ? 1 : 0;
+                y = verdict ? (long)kd : -1;
+            }
+            if (y >= 0) break;
+        }
+    }
+    return flip ? n - y : y;
+}
+
+// G lanes per (resample, POVM): the O outcomes are cut into G contiguous groups, the shots are first split between
+// the groups by a binary tree of binomials over the group masses (log2 G levels: one lane, then two, ...), then
+// every lane runs the conditional-binomial chain over ITS group with the group's shots and mass -- the same
+// multinomial law (the decomposition is exact for any grouping), a chain of log2 G + O/G binomials per thread
+// instead of O - 1.  The chain is what bounds this kernel (a thread's binomials are serial, ~2.7 us each: 1e5 x 36
+// outcomes took 0.19 ms with 0.33 waves of threads, 12 500 x 36 still 0.096 ms).  G depends on O only, and every
+// lane has its own Philox stream (counter word 1 carries the group), so a sample's counts depend neither on the
+// batch nor on the shard it is drawn in.  The last outcome of the LAST group takes the remaining mass 1 - sum(p),
+// as NumPy's multinomial does; the last outcome of any other group takes what is left of the group's shots.
+template <bool PREFILTER, int G>
 __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, const double* __restrict__ p, int batched, ShotVec shots,
                                        uint32_t k0, uint32_t k1, uint64_t offset, int32_t* __restrict__ counts,
                                        int exact_every) {
+    const unsigned full = 0xffffffffu;
     const long items = (long)B * P;
-    for (long item = (long)blockIdx.x * blockDim.x + threadIdx.x; item < items; item += (long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane % G;
+    const int gsize = (O + G - 1) / G;
+    const int o_begin = min(g * gsize, O), o_end = min(o_begin + gsize, O);
+    // warp-uniform trip count: a warp runs while its first item exists; lanes beyond the end draw nothing
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; (t - lane) / G < items; t += (long)gridDim.x * blockDim.x) {
+        const bool live = t / G < items;
+        const long item = live ? t / G : items - 1;
         const long b = item / P;
         const int m = (int)(item % P);
         const double* row = p + (batched ? item : (long)m) * O;
         const uint64_t sample = offset + (uint64_t)b;
         PhiloxStream rng;
         rng.k0 = k0; rng.k1 = k1;
-        rng.c1 = (uint32_t)m | 0x80000000u;  // separate counter domain from the alias sampler
+        rng.c1 = (uint32_t)m | ((uint32_t)g << 16) | 0x80000000u;  // bit 31: separate counter domain from the alias sampler
         rng.c2 = (uint32_t)sample; rng.c3 = (uint32_t)(sample >> 32);
         rng.j = 0; rng.have = false; rng.spare = 0.0;
-        long left = shots.n[m];
+        long left = live ? shots.n[m] : 0;
         double mass = 1.0, po = 0.0;
+        if (G > 1) {
+            // inclusive prefix of the group masses over the item's lanes; the prefix through the last group is 1
+            double pm = 0.0;
+            for (int o = o_begin; o < o_end; ++o) pm += fmin(fmax(row[o], 0.0), 1.0);
+            const double own = pm;
+#pragma unroll
+            for (int dlt = 1; dlt < G; dlt <<= 1) {
+                const double u = __shfl_up_sync(full, pm, dlt, G);
+                if (g >= dlt) pm += u;
+            }
+            if (g == G - 1) pm = 1.0;
+            const double below = __shfl_sync(full, pm, (g + G - 1) % G, G);
+            const double lo = g > 0 ? below : 0.0;
+            mass = g == G - 1 ? 1.0 - lo : own;
+            if (g != 0) left = 0;  // lane 0 holds the item's shots; the tree hands them down
+#pragma unroll
+            for (int width = G; width > 1; width >>= 1) {
+                const int half = width >> 1;
+                const bool splits = (g % width) == 0;
+                const double mid = __shfl_sync(full, pm, (g + half - 1) % G, G);
+                const double hi = __shfl_sync(full, pm, (g + width - 1) % G, G);
+                long to_right = 0;
+                if (splits) {
+                    const double whole = hi - lo, part = mid - lo;
+                    const double cond = whole > 0.0 ? fmin(fmax(part * fast_recip(whole), 0.0), 1.0) : 1.0;
+                    const long n_left = binomial_variate<PREFILTER>(left, cond, rng);
+                    to_right = left - n_left;
+                    left = n_left;
+                }
+                const long got = __shfl_sync(full, to_right, (g + G - half) % G, G);
+                if ((g % width) == half) left = got;
+            }
+        }
         int32_t* out = counts + item * O;
         // Per-lane state machine: every trip of the loop is ONE proposal of the lane's current binomial, so
         // the lanes of a warp walk through their outcome sequences independently instead of waiting for the
@@ -314,8 +392,8 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, cons
         Btrs st;
         bool flip = false, ready = false, pending = false;
         double cand = 0.0, cv = 0.0, cus = 0.0;  // undecided candidate and its (v, us)
-        int o = 0, trip = 0;
-        while (o + 1 < O) {
+        int o = o_begin, trip = 0;
+        while (o + 1 < o_end) {
             ++trip;
             if (!ready) {  // set up the lane's next binomial, then fall through to its first proposal
                 po = fmin(fmax(row[o], 0.0), 1.0);
@@ -336,7 +414,7 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, cons
                     }
                 }
                 if (c >= 0) {
-                    out[o] = (int32_t)c;
+                    if (live) out[o] = (int32_t)c;
                     left -= c;
                     mass -= po;
                     ++o;
@@ -355,14 +433,14 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, cons
             }
             if (y >= 0) {
                 const long c = flip ? left - y : y;
-                out[o] = (int32_t)c;
+                if (live) out[o] = (int32_t)c;
                 left -= c;
                 mass -= po;
                 ++o;
                 ready = false;
             }
         }
-        out[O - 1] = (int32_t)left;
+        if (live && o_end > o_begin) out[o_end - 1] = (int32_t)left;
     }
 }
 
@@ -395,28 +473,41 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
         const long items = (long)B * P;
         const int every = option(QPB_OPT_SAMPLER_EXACT_EVERY) > 0 ? option(QPB_OPT_SAMPLER_EXACT_EVERY) : kExactEvery;
         const bool prefilter = !option(QPB_OPT_SAMPLER_NO_PREFILTER);
-        auto kern = prefilter ? k_multinomial_binomial<true> : k_multinomial_binomial<false>;
+        // lanes per item: it must not depend on the batch (the counts would), and measured on B200 (tools/
+        // sampler_sweep.py, 36 outcomes) four lanes take 0.060 ms instead of 0.096 ms for 12 500 items but 0.233 ms
+        // instead of 0.191 ms for 1e5 (idle lanes during the splits, shorter chains diverge more): one lane unless asked
+        int G = option(QPB_OPT_SAMPLER_LANES) > 0 ? option(QPB_OPT_SAMPLER_LANES) : 1;
+        QPB_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8, "SAMPLER_LANES must be 1, 2, 4 or 8");
+        while (G > 1 && (G - 1) * ((O + G - 1) / G) >= O - 1) G >>= 1;  // the last group needs two outcomes of its own
+        typedef void (*kern_t)(int, int, int, const double*, int, ShotVec, uint32_t, uint32_t, uint64_t, int32_t*, int);
+        static const kern_t table[2][4] = {
+            {k_multinomial_binomial<false, 1>, k_multinomial_binomial<false, 2>, k_multinomial_binomial<false, 4>,
+             k_multinomial_binomial<false, 8>},
+            {k_multinomial_binomial<true, 1>, k_multinomial_binomial<true, 2>, k_multinomial_binomial<true, 4>,
+             k_multinomial_binomial<true, 8>}};
+        const int gi = G == 1 ? 0 : (G == 2 ? 1 : (G == 4 ? 2 : 3));
+        kern_t kern = table[prefilter][gi];
         // Every thread walks its O - 1 binomials from start to end, so a launch that needs one block more than fits
         // takes twice as long: pick the largest block size whose grid is resident at once (1e5 items: 782 blocks of 128
         // against 740 slots, but 1563 blocks of 64 against 1628), else 128 and a grid-stride loop
-        static int occ[2][3] = {{0, 0, 0}, {0, 0, 0}};  // resident blocks per SM for 128 / 96 / 64 threads
+        static int occ[2][4][3] = {};  // resident blocks per SM for 128 / 96 / 64 threads
         const int cand[3] = {128, 96, 64};
         int threads = option(QPB_OPT_SAMPLER_THREADS) > 0 ? option(QPB_OPT_SAMPLER_THREADS) : 0;
         if (threads == 0) {
             threads = 128;
             for (int c = 0; c < 3; ++c) {
-                if (occ[prefilter][c] == 0) {
+                if (occ[prefilter][gi][c] == 0) {
                     int nb = 0;
                     QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, cand[c], 0));
-                    occ[prefilter][c] = nb > 0 ? nb : 1;
+                    occ[prefilter][gi][c] = nb > 0 ? nb : 1;
                 }
-                if ((items + cand[c] - 1) / cand[c] <= (long)num_sms() * occ[prefilter][c]) {
+                if ((items * G + cand[c] - 1) / cand[c] <= (long)num_sms() * occ[prefilter][gi][c]) {
                     threads = cand[c];
                     break;
                 }
             }
         }
-        long blocks = (items + threads - 1) / threads;
+        long blocks = (items * G + threads - 1) / threads;
         const long cap = (long)num_sms() * 16;
         if (blocks > cap) blocks = cap;
         kern<<<(int)blocks, threads, 0, st>>>(B, P, O, p, p_batched, shots, (uint32_t)seed, (uint32_t)(seed >> 32), offset,

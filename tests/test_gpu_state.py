@@ -76,12 +76,14 @@ def test_probabilities_match_reference(qp, golden, case):
     assert np.abs(p - g["probs"]).max() < 1e-14
 
 
-@pytest.fixture(params=["binomial", "alias"])
+@pytest.fixture(params=["binomial", "alias", "binomial-4-lanes", "binomial-8-lanes"])
 def sampler_kind(request):
-    """Both multinomial kernels are held to the same distributional tests (the SAMPLER option forces one)."""
+    """Both multinomial kernels -- and the conditional-binomial one with its outcomes split over 4 / 8 lanes per
+    item (a binary tree of group splits first: SAMPLER_LANES) -- are held to the same distributional tests."""
     from quantpy_b200 import _native as nt
 
-    with nt.option("SAMPLER", nt.SAMPLERS[request.param]):
+    kind, _, lanes = request.param.partition("-")
+    with nt.option("SAMPLER", nt.SAMPLERS[kind]), nt.option("SAMPLER_LANES", int(lanes[0]) if lanes else 0):
         yield request.param
 
 
