@@ -506,7 +506,7 @@ class StateWorkload:
         return itv
 
     def e2e_h2d(self):
-        if self.gpu.world == 1 and self.gpu.engine.FUSED_INTERVAL:
+        if self.gpu.engine.FUSED_INTERVAL:
             return 0  # one library call uploads Bloch vector, centre state and levels; counted in parallel.TRAFFIC
         return self.state.bloch.size * 8 + self.ref.numel() * 8
 

@@ -74,7 +74,7 @@ def _all_gather_padded(local, n_total):
     return gathered, width
 
 
-def gather_sorted(local, n_total):
+def gather_sorted(local, n_total, presorted=False):
     """The sorted vector of all ranks' values (what the reference gets from `dist.sort()`, interval.py:610): every
     rank sorts its own shard, ONE all-gather collects the sorted shards, and a counting merge of the world_size
     runs (qpb_merge_sorted_runs, one launch) replaces a second full sort on every rank.  CUDA tensors only; the
@@ -83,7 +83,7 @@ def gather_sorted(local, n_total):
     if not local.is_cuda:
         import torch
 
-        return torch.sort(all_gather_concat(local, n_total)).values
+        return torch.sort(all_gather_concat(local, n_total)).values  # (a presorted shard changes nothing here)
     import ctypes
 
     import torch
@@ -91,7 +91,7 @@ def gather_sorted(local, n_total):
     from . import _native as nt
     from . import engine
 
-    mine = engine.sort_f64(local)
+    mine = local if presorted else engine.sort_f64(local)
     if size == 1:
         return mine
     gathered, width = _all_gather_padded(mine, n_total)

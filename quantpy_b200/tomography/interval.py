@@ -148,18 +148,22 @@ class BootstrapStateInterval(ConfidenceInterval):
         seed = parallel.broadcast_seed(engine.next_seed()) if seed is None else int(seed)
         plan = engine.state_plan(self.tmg.povm_matrix, self.tmg.n_measurements)
         kind = dst_kind(self.tmg.dst)
-        if size == 1 and kind is not None and self.n_points >= 1 and engine.FUSED_INTERVAL:
-            # one GPU, built-in distance: ONE library call with host inputs and outputs (qpb_bootstrap_state_interval)
+        if kind is not None and hi > lo and engine.FUSED_INTERVAL:
+            # built-in distance: ONE library call with host inputs and outputs (qpb_bootstrap_state_interval) runs this
+            # rank's shard -- upload, probabilities, bootstrap, shard sort and, on one GPU, the quantiles as well
             levels = np.linspace(1e-3, 1 - 1e-3, 1000) if conf_levels is None else np.asarray(conf_levels, dtype=np.float64)
-            if np.any(levels < 0) or np.any(levels > 1):
-                levels = np.zeros(0)  # let cl_to_dist raise interp1d's error when it is called
+            if size > 1 or np.any(levels < 0) or np.any(levels > 1):
+                levels = np.zeros(0)  # several GPUs: after the gather; bad levels: cl_to_dist raises interp1d's error
             q, dist, self._iters_dev = engine.bootstrap_interval(
-                plan, self.state.bloch, self.state.matrix, self.n_points, seed, 0, method, self.physical, self.init,
+                plan, self.state.bloch, self.state.matrix, hi - lo, seed, lo, method, self.physical, self.init,
                 self.max_iter, self.tol, kind, levels)
             parallel.TRAFFIC["h2d"] += (3 * plan.D + levels.size) * 8
             parallel.TRAFFIC["d2h"] += levels.size * 8
+            if size > 1:
+                dist = parallel.gather_sorted(dist, self.n_points, presorted=True)
             self.cl_to_dist = parallel.quantile_function(dist, presorted=True)
-            self.cl_to_dist.prime(levels, q.reshape(levels.shape))
+            if size == 1:
+                self.cl_to_dist.prime(levels, q.reshape(levels.shape))
             return
         probs = plan.probabilities(self.state.bloch)[0]
         out = plan.bootstrap(probs, hi - lo, seed, lo, self.state.matrix, method, self.physical, self.init,
