@@ -559,7 +559,7 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
         const int32_t* crow = a.counts + b * K;
         const int c0 = lane < K ? crow[lane] : 0;
         const int c1 = (32 + lane) < K ? crow[32 + lane] : 0;
-        int tot = c0 + c1;
+        long long tot = (long long)c0 + c1;  // 64-bit, like the thread-per-sample refill: P * shots may pass 2^31
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(full, tot, o);
         const FreqDiv freq((double)tot);
