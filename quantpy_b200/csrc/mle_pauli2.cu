@@ -148,6 +148,9 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+// reciprocal of a probability (+ guard) for the likelihood weight: one Newton step (common.cuh); both lane mappings
+// call this one function
+__device__ __forceinline__ double weight_recip(double q) { return fast_recip_1step(q); }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -249,10 +252,11 @@ __device__ __forceinline__ void iterate(const PauliParams& pp, const double (&h)
             w[be] = q;
         }
 #pragma unroll
-        for (int be = 0; be < 6; ++be) w[be] = dmul(fcol[(al * 6 + be) * fstride], fast_recip(w[be]));
+        for (int be = 0; be < 6; ++be) w[be] = dmul(fcol[(al * 6 + be) * fstride], weight_recip(w[be]));
         const double y0 = dadd(dadd(dadd(w[0], w[1]), dadd(w[2], w[3])), dadd(w[4], w[5]));
-        N[al][0] = dadd(y0, dsub(w[4], w[5]));
-        N[al][1] = dadd(y0, dsub(w[5], w[4]));
+        const double dz = dsub(w[4], w[5]);
+        N[al][0] = dadd(y0, dz);
+        N[al][1] = dsub(y0, dz);  // = y0 + (w5 - w4) bit for bit (w5 - w4 is the exact negative of w4 - w5)
         N[al][2] = dsub(w[0], w[1]);
         N[al][3] = dsub(w[3], w[2]);
     }
@@ -261,8 +265,9 @@ __device__ __forceinline__ void iterate(const PauliParams& pp, const double (&h)
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         const double y0 = dadd(dadd(dadd(N[0][c], N[1][c]), dadd(N[2][c], N[3][c])), dadd(N[4][c], N[5][c]));
-        const double d0 = dadd(y0, dsub(N[4][c], N[5][c]));  // block (0,0)
-        const double d1 = dadd(y0, dsub(N[5][c], N[4][c]));  // block (1,1)
+        const double dz = dsub(N[4][c], N[5][c]);
+        const double d0 = dadd(y0, dz);  // block (0,0)
+        const double d1 = dsub(y0, dz);  // block (1,1): y0 + (N5 - N4), the same bits
         if (c == 0) { Rr[0][0] = d0; Rr[2][2] = d1; }
         if (c == 1) { Rr[1][1] = d0; Rr[3][3] = d1; }
         if (c == 2) { Rr[0][1] = Rr[1][0] = d0; Rr[2][3] = Rr[3][2] = d1; }
@@ -341,8 +346,9 @@ __device__ __forceinline__ double normalise_step(const double (&hn)[16], double 
         const int e0 = 2 * j, e1 = 2 * j + 1;
         const double x0 = dmul(hn[e0], inv), x1 = dmul(hn[e1], inv);
         const double d0 = dsub(x0, h[e0]), d1 = dsub(x1, h[e1]);
-        const double m0 = (e0 / 4 == e0 % 4) ? 1.0 : 2.0, m1 = (e1 / 4 == e1 % 4) ? 1.0 : 2.0;
-        p[j] = dfma(dmul(m1, d1), d1, dmul(dmul(m0, d0), d0));
+        // weights 1 (diagonal) or 2 (the pair (a,b), (b,a)): a product with 1.0 is the operand itself
+        const double w0 = (e0 / 4 == e0 % 4) ? d0 : dmul(2.0, d0), w1 = (e1 / 4 == e1 % 4) ? d1 : dmul(2.0, d1);
+        p[j] = dfma(w1, d1, dmul(w0, d0));
         h[e0] = x0;
         h[e1] = x1;
     }
@@ -612,12 +618,12 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
                     const double v = dadd(wb[qb0], flip(wb[qab0], q1neg0));
                     double q = dadd(u, flip(v, q2neg0));
                     if (!UG) q = dadd(q, eps0);
-                    const double w0 = dmul(wb[F + lane], fast_recip(q));
+                    const double w0 = dmul(wb[F + lane], weight_recip(q));
                     const double u1 = dadd(s00, flip(wb[qa1], q1neg1));
                     const double v1 = dadd(wb[qb1], flip(wb[qab1], q1neg1));
                     double q1 = dadd(u1, flip(v1, q2neg1));
                     if (!UG) q1 = dadd(q1, eps1);
-                    const double w1 = dmul(wb[F + 32 + (lane & 3)], fast_recip(q1));
+                    const double w1 = dmul(wb[F + 32 + (lane & 3)], weight_recip(q1));
                     wb[W + lane] = w0;
                     if (lane < 4) wb[W + 32 + lane] = w1;
                 }
