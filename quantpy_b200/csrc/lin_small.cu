@@ -96,7 +96,10 @@ __device__ __forceinline__ double lin_project_one(int K, long b, const double* _
                                                   double* __restrict__ rho);
 
 template <int N>
-__global__ void __launch_bounds__(kLinThreads)
+#ifndef LIN_MIN_BLOCKS
+#define LIN_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(kLinThreads, LIN_MIN_BLOCKS)
 k_lin_project_small(int K, int B, const double* __restrict__ LhT, const int32_t* __restrict__ counts, int physical,
                     double* __restrict__ rho, unsigned char* __restrict__ class_out, unsigned int* __restrict__ class_hist) {
     constexpr int d = 1 << N, D = d * d;
