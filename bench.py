@@ -13,9 +13,12 @@ The headline workload is BASELINE.json configs[1] (`--config c2`, the default: 2
 global index range (weak scaling, no data-path collective).  The JSON line also carries
 
 `e2e`       the same metric through the public API (Bootstrap*Interval.setup() + cl_to_dist) with host inputs
-            and host outputs inside the timed region (the all-gather + quantile step included); `e2e.dist_on_host`
-            is the figure with all N sorted distances copied to the host as well (the reference's `cl_to_dist`
-            owns them there).
+            and host outputs inside the timed region (the all-gather + quantile step included).  For the state
+            interval the API makes ONE C-ABI call per rank with host buffers on both sides
+            (qpb_bootstrap_state_interval: upload, probabilities, bootstrap, sort, quantiles, download).  Every rank
+            times its own calls (each returns after a stream synchronisation); the figure is the MAX over ranks.
+            `e2e.dist_on_host` is the figure with all N sorted distances copied to the host as well (the
+            reference's `cl_to_dist` owns them there).
 `strong`    BASELINE configs[1] as written: 1e5 resamples GLOBALLY, sharded over the N ranks, with the sort of the
             shard, the all-gather and the merge of the sorted shards inside the CUDA-event-timed region.
 `roofline`  for the dominant kernel of the config, timed alone: executed work / duration against a peak measured
@@ -742,10 +745,12 @@ def measure(gpu, cfg, steps, warmup, e2e_steps, with_cpu, cpu_seconds, with_roof
         t0 = time.perf_counter()
         itv = wl.interval(B * world, seed=wl.seed + 100 + i)
         _ = itv.cl_to_dist(levels)       # the result a user reads: distances at the confidence levels, on the host
-        gpu.barrier()
+        # the call returned after a stream synchronisation with its result on this rank's host; its all-gather has
+        # already tied the ranks together, and the reported time is the MAX over ranks of each rank's own sum
         t1 = time.perf_counter()
         _ = itv.dist                     # ... and all N sorted distances, as the reference's cl_to_dist owns them
         t2 = time.perf_counter()
+        gpu.barrier()
         if i >= warm_calls:
             times.append(t1 - t0)
             times_full.append(t2 - t0)
