@@ -506,6 +506,8 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
         else if (ra < rb) out_src = rb * 4 + ra;
         else { out_src = ra * 4 + rb; out_neg = 1; }
     }
+    const unsigned pair_neg = (lane & 2) ? 0u : 1u;  // the product pairs: lanes with bit 1 clear hold a difference
+    const unsigned hi_half = lane < 16 ? 0u : 1u;   // second product: the imaginary half takes -R
     const double tol2 = a.tol * a.tol;
     const int K = pp.K;
     if (lane == 0) wb[ZERO] = 0.0;
@@ -666,20 +668,21 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
                     double d0 = 0.0, d1 = 0.0;
                     dmma(d0, d1, val, bfrag);
                     const double p0 = __shfl_xor_sync(full, d0, 18), p1 = __shfl_xor_sync(full, d1, 18);
-                    const double r0 = (lane & 2) ? dadd(d0, p0) : dsub(d0, p0);
-                    const double r1 = (lane & 2) ? dadd(d1, p1) : dsub(d1, p1);
+                    // lanes with bit 1 clear subtract: d - p = d + (-p) bit for bit, the sign flips on the integer pipe
+                    const double r0 = dadd(d0, flip(p0, pair_neg));
+                    const double r1 = dadd(d1, flip(p1, pair_neg));
                     if (lane < 16) *reinterpret_cast<double2*>(wb + xo) = make_double2(r0, r1);
                 }
                 __syncwarp();
                 // -- P4: second product -> unnormalised new state ---------------------------------------------
                 {
                     const double a2 = wb[X + lane];
-                    const double b2 = lane < 16 ? val : -val;
+                    const double b2 = flip(val, hi_half);
                     double d0 = 0.0, d1 = 0.0;
                     dmma(d0, d1, a2, b2);
                     const double p0 = __shfl_xor_sync(full, d0, 18), p1 = __shfl_xor_sync(full, d1, 18);
-                    const double r0 = (lane & 2) ? dadd(d0, p0) : dsub(d0, p0);
-                    const double r1 = (lane & 2) ? dadd(d1, p1) : dsub(d1, p1);
+                    const double r0 = dadd(d0, flip(p0, pair_neg));
+                    const double r1 = dadd(d1, flip(p1, pair_neg));
                     if (ho0 >= 0) wb[ho0] = r0;
                     if (ho1 >= 0) wb[ho1] = r1;
                 }
@@ -1217,14 +1220,17 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
             // measured on B200 (tools/pauli2_sweep_d.py, C2 workload): the fuller the thread-per-sample lanes, the
             // less W capacity is left, so the hand-over age rises with the batch: 200 / 300 / 450 iterations
             const long long lanes = (long long)sms * max_sw * 32;
-            const int age = (long long)B * 2 <= lanes ? 200 : ((long long)B * 2 <= lanes * 3 ? 300 : 500);
+            // (tools/pauli2_sweep_n.py: below half a wave of lanes a late general age with an early start for the first
+            // queue positions beats the early general age: 12 500 samples 0.788 -> 0.710 ms per step)
+            const bool half_wave = (long long)B * 2 <= lanes;
+            const int age = (long long)B * 2 <= lanes * 3 ? 300 : 500;
             a.park_age = option(QPB_OPT_MLE_PARK_AGE) > 0 ? option(QPB_OPT_MLE_PARK_AGE) : age;
             {
                 // measured on B200 (tools/pauli2_sweep_h.py): while most of the batch starts in the first wave of
                 // lanes a broad ramp from 250 pays; with several waves the W workers are too few for that
                 const bool few_waves = (long long)B * 2 <= lanes * 3;
                 const int lo = option(QPB_OPT_MLE_PARK_AGE_LO), pct = option(QPB_OPT_MLE_PARK_AGE_PCT);
-                a.park_age_lo = lo > 0 ? lo : (lo < 0 ? a.park_age : (few_waves ? 250 : 350));
+                a.park_age_lo = lo > 0 ? lo : (lo < 0 ? a.park_age : (half_wave ? 100 : (few_waves ? 250 : 350)));
                 if (a.park_age_lo > a.park_age) a.park_age_lo = a.park_age;
                 const double frac = (pct > 0 ? pct : (few_waves ? 50 : 10)) / 100.0;
                 a.park_age_slope = (float)((a.park_age - a.park_age_lo) / (frac * (double)B));
@@ -1235,7 +1241,7 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
                 const double span = (pct2 > 0 ? pct2 : 50) / 100.0 * (double)(B - a.park_q2) + 1.0;
                 a.park_age_slope2 = (float)((a.park_age - a.park_age_end) / span);
             }
-            a.park_live = option(QPB_OPT_MLE_PARK_LIVE) > 0 ? option(QPB_OPT_MLE_PARK_LIVE) : ((long long)B * 4 <= lanes ? 16 : 5);
+            a.park_live = option(QPB_OPT_MLE_PARK_LIVE) > 0 ? option(QPB_OPT_MLE_PARK_LIVE) : (half_wave ? 20 : 5);
             if (a.single_warps < max_sw || a.single_warps + w_warps > kPauliWarps) w_warps = kPauliWarps - a.single_warps;
             const int poll = option(QPB_OPT_MLE_TAIL_POLL);
             a.tail_poll = poll < 0 ? 0 : (poll == 0 ? 4 : poll);
