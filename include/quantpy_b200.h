@@ -79,7 +79,7 @@ enum {
     QPB_OPT_SAMPLER_EXACT_EVERY = 31,  /* binomial sampler tuning: undecided candidates are tested on loop trips that are multiples of this (0 = default) */
     QPB_OPT_SAMPLER_THREADS = 32,      /* binomial sampler tuning: threads per block (0 = chosen so that the launch is one wave when it can be) */
     QPB_OPT_NO_SAMPLE_SORT = 33,       /* qpb_sort_f64: the earlier path (one-CTA bitonic network up to 16384 keys, device radix sort above) instead of counting / sample sort */
-    QPB_OPT_SAMPLER_LANES = 34,        /* binomial sampler: lanes per (resample, POVM): 1, 2, 4 or 8 (0 = by the number of outcomes); changes the random stream, not the law */
+    QPB_OPT_SAMPLER_LANES = 34,        /* binomial sampler: groups of outcomes per (resample, POVM), one thread each after a pass that splits the shots between the groups (0 = by the number of outcomes, 1 = a single chain); changes the random stream, not the law */
     QPB_OPT_COUNT_ = 35
 };
 QPB_API int qpb_set_option(int which, int value);

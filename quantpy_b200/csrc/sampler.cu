@@ -290,102 +290,69 @@ struct Btrs {
 // period 1: 0.195 ms, 2: 0.183 ms, 3: 0.197 ms, 4: 0.216 ms (waiting lanes cost more than the saved long paths).
 constexpr int kExactEvery = 2;
 
-// One Binomial(n, p) variate, blocking (the group splits of the lanes-per-item decomposition below).
-template <bool PREFILTER>
-__device__ long binomial_variate(long n, double p, PhiloxStream& rng) {
-    if (n <= 0 || !(p > 0.0)) return 0;
-    if (p >= 1.0) return n;
-    const bool flip = p > 0.5;
-    const double r = flip ? 1.0 - p : p;
-    if (!(r > 0.0)) return flip ? n : 0;
-    long y;
-    if ((double)n * r < 10.0) {
-        y = binomial_inversion(n, r, rng);
-    } else {
-        Btrs st;
-        st.setup(n, r);
-        for (;;) {
-            double kd, v, us;
-            y = st.propose(rng, kd, v, us);
-            if (y == -2) {
-                int verdict = PREFILTER ? st.accept_quick(kd, v, us) : -1;
-                if (verdict < 0) verdict = st.accept_exact(kd, v, us) ? 1 : 0;
-                y = verdict ? (long)kd : -1;
-            }
-            if (y >= 0) break;
-        }
-    }
-    return flip ? n - y : y;
-}
-
-// G lanes per (resample, POVM): the O outcomes are cut into G contiguous groups, the shots are first split between
-// the groups by a binary tree of binomials over the group masses (log2 G levels: one lane, then two, ...), then
-// every lane runs the conditional-binomial chain over ITS group with the group's shots and mass -- the same
-// multinomial law (the decomposition is exact for any grouping), a chain of log2 G + O/G binomials per thread
-// instead of O - 1.  The chain is what bounds this kernel (a thread's binomials are serial, ~2.7 us each: 1e5 x 36
-// outcomes took 0.19 ms with 0.33 waves of threads, 12 500 x 36 still 0.096 ms).  G depends on O only, and every
-// lane has its own Philox stream (counter word 1 carries the group), so a sample's counts depend neither on the
-// batch nor on the shard it is drawn in.  The last outcome of the LAST group takes the remaining mass 1 - sum(p),
-// as NumPy's multinomial does; the last outcome of any other group takes what is left of the group's shots.
-template <bool PREFILTER, int G>
-__global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, const double* __restrict__ p, int batched, ShotVec shots,
-                                       uint32_t k0, uint32_t k1, uint64_t offset, int32_t* __restrict__ counts,
+// Conditional-binomial chain over "outcomes" [o_begin, o_end) of one (resample, POVM) item -- the whole table
+// (MODE 0), its G groups of consecutive outcomes taken as G coarse outcomes (MODE 1), or the outcomes of ONE group
+// with the shots the coarse pass gave it (MODE 2).
+//
+// Two passes instead of one (G > 1): pass 1 splits the item's shots between G groups of ~O/G consecutive outcomes
+// (one thread per item, G - 1 binomials over the group masses), pass 2 runs the chain inside every group (one thread
+// per (item, group), O/G - 1 binomials).  The law is the same multinomial (conditioning on group totals is exact), the
+// number of binomials per item is the same, but a thread's SERIAL chain -- which is what bounds this kernel: ~2.7 us
+// per binomial, 35 of them at 36 outcomes -- is G - 1 + O/G - 1 long instead of O - 1, and pass 2 has G times the
+// threads to hide its fixed-latency dependencies with.  G depends on O only and every (item, group) has its own
+// Philox stream (counter word 1: bits 16-23 carry the pass / group), so a sample's counts depend neither on the batch
+// nor on the shard it is drawn in.  The last outcome of the last group takes the remaining mass 1 - sum(p), as NumPy's
+// multinomial does (state.py:112); the last outcome of any other group takes what is left of the group's shots.
+template <bool PREFILTER, int MODE>
+__global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, int G, const double* __restrict__ p, int batched,
+                                       ShotVec shots, uint32_t k0, uint32_t k1, uint64_t offset,
+                                       int32_t* __restrict__ counts, int32_t* __restrict__ group_counts,
                                        int exact_every) {
-    const unsigned full = 0xffffffffu;
     const long items = (long)B * P;
-    const int lane = threadIdx.x & 31;
-    const int g = lane % G;
+    const long work = MODE == 2 ? items * G : items;
     const int gsize = (O + G - 1) / G;
-    const int o_begin = min(g * gsize, O), o_end = min(o_begin + gsize, O);
-    // warp-uniform trip count: a warp runs while its first item exists; lanes beyond the end draw nothing
-    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; (t - lane) / G < items; t += (long)gridDim.x * blockDim.x) {
-        const bool live = t / G < items;
-        const long item = live ? t / G : items - 1;
+    for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < work; t += (long)gridDim.x * blockDim.x) {
+        const long item = MODE == 2 ? t / G : t;
+        const int g = MODE == 2 ? (int)(t % G) : 0;
         const long b = item / P;
         const int m = (int)(item % P);
         const double* row = p + (batched ? item : (long)m) * O;
         const uint64_t sample = offset + (uint64_t)b;
         PhiloxStream rng;
         rng.k0 = k0; rng.k1 = k1;
-        rng.c1 = (uint32_t)m | ((uint32_t)g << 16) | 0x80000000u;  // bit 31: separate counter domain from the alias sampler
+        // bit 31: counter domain separate from the alias sampler; bits 16-23: 0 whole table, 255 group pass, 1 + g group g
+        rng.c1 = (uint32_t)m | ((uint32_t)(MODE == 0 ? 0 : (MODE == 1 ? 255 : 1 + g)) << 16) | 0x80000000u;
         rng.c2 = (uint32_t)sample; rng.c3 = (uint32_t)(sample >> 32);
         rng.j = 0; rng.have = false; rng.spare = 0.0;
-        long left = live ? shots.n[m] : 0;
+        // probability of "outcome" o: a table entry, or (MODE 1) the mass of group o, summed in index order
+        auto prob = [&](int o) -> double {
+            if (MODE != 1) return fmin(fmax(row[o], 0.0), 1.0);
+            double s = 0.0;
+            const int e = min((o + 1) * gsize, O);
+            for (int i = o * gsize; i < e; ++i) s += fmin(fmax(row[i], 0.0), 1.0);
+            return s;
+        };
+        int o_begin = 0, o_end = MODE == 1 ? G : O;
+        long left = shots.n[m];
         double mass = 1.0, po = 0.0;
-        if (G > 1) {
-            // inclusive prefix of the group masses over the item's lanes; the prefix through the last group is 1
-            double pm = 0.0;
-            for (int o = o_begin; o < o_end; ++o) pm += fmin(fmax(row[o], 0.0), 1.0);
-            const double own = pm;
-#pragma unroll
-            for (int dlt = 1; dlt < G; dlt <<= 1) {
-                const double u = __shfl_up_sync(full, pm, dlt, G);
-                if (g >= dlt) pm += u;
-            }
-            if (g == G - 1) pm = 1.0;
-            const double below = __shfl_sync(full, pm, (g + G - 1) % G, G);
-            const double lo = g > 0 ? below : 0.0;
-            mass = g == G - 1 ? 1.0 - lo : own;
-            if (g != 0) left = 0;  // lane 0 holds the item's shots; the tree hands them down
-#pragma unroll
-            for (int width = G; width > 1; width >>= 1) {
-                const int half = width >> 1;
-                const bool splits = (g % width) == 0;
-                const double mid = __shfl_sync(full, pm, (g + half - 1) % G, G);
-                const double hi = __shfl_sync(full, pm, (g + width - 1) % G, G);
-                long to_right = 0;
-                if (splits) {
-                    const double whole = hi - lo, part = mid - lo;
-                    const double cond = whole > 0.0 ? fmin(fmax(part * fast_recip(whole), 0.0), 1.0) : 1.0;
-                    const long n_left = binomial_variate<PREFILTER>(left, cond, rng);
-                    to_right = left - n_left;
-                    left = n_left;
+        int32_t* out = MODE == 1 ? group_counts + item * G : counts + item * O;
+        if (MODE == 2) {
+            o_begin = min(g * gsize, O);
+            o_end = min(o_begin + gsize, O);
+            left = group_counts[item * G + g];
+            // the group's mass as pass 1 saw it: its own sum, or for the last group what the others leave of 1
+            mass = 0.0;
+            if (g == G - 1) {
+                for (int gg = 0; gg < G - 1; ++gg) {
+                    double s = 0.0;
+                    for (int i = gg * gsize; i < (gg + 1) * gsize; ++i) s += fmin(fmax(row[i], 0.0), 1.0);
+                    mass += s;
                 }
-                const long got = __shfl_sync(full, to_right, (g + G - half) % G, G);
-                if ((g % width) == half) left = got;
+                mass = 1.0 - mass;
+            } else {
+                for (int i = o_begin; i < o_end; ++i) mass += fmin(fmax(row[i], 0.0), 1.0);
             }
         }
-        int32_t* out = counts + item * O;
         // Per-lane state machine: every trip of the loop is ONE proposal of the lane's current binomial, so
         // the lanes of a warp walk through their outcome sequences independently instead of waiting for the
         // slowest rejection loop at every outcome.
@@ -396,7 +363,7 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, cons
         while (o + 1 < o_end) {
             ++trip;
             if (!ready) {  // set up the lane's next binomial, then fall through to its first proposal
-                po = fmin(fmax(row[o], 0.0), 1.0);
+                po = prob(o);
                 long c = -1;
                 if (left <= 0 || !(po > 0.0)) {
                     c = 0;
@@ -414,7 +381,7 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, cons
                     }
                 }
                 if (c >= 0) {
-                    if (live) out[o] = (int32_t)c;
+                    out[o] = (int32_t)c;
                     left -= c;
                     mass -= po;
                     ++o;
@@ -433,14 +400,14 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, cons
             }
             if (y >= 0) {
                 const long c = flip ? left - y : y;
-                if (live) out[o] = (int32_t)c;
+                out[o] = (int32_t)c;
                 left -= c;
                 mass -= po;
                 ++o;
                 ready = false;
             }
         }
-        if (live && o_end > o_begin) out[o_end - 1] = (int32_t)left;
+        if (o_end > o_begin) out[o_end - 1] = (int32_t)left;
     }
 }
 
@@ -471,48 +438,56 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
     if (force == 2) use_binomial = true;
     if (use_binomial) {
         const long items = (long)B * P;
-        const int every = option(QPB_OPT_SAMPLER_EXACT_EVERY) > 0 ? option(QPB_OPT_SAMPLER_EXACT_EVERY) : kExactEvery;
+        int every = option(QPB_OPT_SAMPLER_EXACT_EVERY) > 0 ? option(QPB_OPT_SAMPLER_EXACT_EVERY) : 0;
         const bool prefilter = !option(QPB_OPT_SAMPLER_NO_PREFILTER);
-        // lanes per item: it must not depend on the batch (the counts would), and measured on B200 (tools/
-        // sampler_sweep.py, 36 outcomes) four lanes take 0.060 ms instead of 0.096 ms for 12 500 items but 0.233 ms
-        // instead of 0.191 ms for 1e5 (idle lanes during the splits, shorter chains diverge more): one lane unless asked
-        int G = option(QPB_OPT_SAMPLER_LANES) > 0 ? option(QPB_OPT_SAMPLER_LANES) : 1;
-        QPB_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8, "SAMPLER_LANES must be 1, 2, 4 or 8");
-        while (G > 1 && (G - 1) * ((O + G - 1) / G) >= O - 1) G >>= 1;  // the last group needs two outcomes of its own
-        typedef void (*kern_t)(int, int, int, const double*, int, ShotVec, uint32_t, uint32_t, uint64_t, int32_t*, int);
-        static const kern_t table[2][4] = {
-            {k_multinomial_binomial<false, 1>, k_multinomial_binomial<false, 2>, k_multinomial_binomial<false, 4>,
-             k_multinomial_binomial<false, 8>},
-            {k_multinomial_binomial<true, 1>, k_multinomial_binomial<true, 2>, k_multinomial_binomial<true, 4>,
-             k_multinomial_binomial<true, 8>}};
-        const int gi = G == 1 ? 0 : (G == 2 ? 1 : (G == 4 ? 2 : 3));
-        kern_t kern = table[prefilter][gi];
-        // Every thread walks its O - 1 binomials from start to end, so a launch that needs one block more than fits
-        // takes twice as long: pick the largest block size whose grid is resident at once (1e5 items: 782 blocks of 128
-        // against 740 slots, but 1563 blocks of 64 against 1628), else 128 and a grid-stride loop
-        static int occ[2][4][3] = {};  // resident blocks per SM for 128 / 96 / 64 threads
+        // groups per item: a function of O alone (the counts must not depend on the batch), about a dozen outcomes per
+        // group.  Measured on B200 at 36 outcomes (tools/sampler_sweep.py, profiles/r2c_sampler_groups.log): 1e5 items
+        // 0.197 ms as one chain, 0.196 ms in 3 groups, 0.231 in 6 (the launch is issue-bound there: same number of
+        // binomials); 12 500 items 0.097 -> 0.069 ms (chain-bound: 2 + 11 binomials per thread instead of 35)
+        int G = O / 12 < 1 ? 1 : (O / 12 > 8 ? 8 : O / 12);
+        if (option(QPB_OPT_SAMPLER_LANES) > 0) G = option(QPB_OPT_SAMPLER_LANES);
+        QPB_REQUIRE(G >= 1 && G <= 64, "SAMPLER_LANES (groups per item) must be in 1..64");
+        while (G > 1 && (G - 1) * ((O + G - 1) / G) >= O - 1) --G;  // the last group keeps two outcomes of its own
+        if (every == 0) every = G > 1 ? 1 : kExactEvery;  // short chains: waiting for an even trip costs more than it saves
+        typedef void (*kern_t)(int, int, int, int, const double*, int, ShotVec, uint32_t, uint32_t, uint64_t, int32_t*,
+                               int32_t*, int);
+        static const kern_t table[2][3] = {
+            {k_multinomial_binomial<false, 0>, k_multinomial_binomial<false, 1>, k_multinomial_binomial<false, 2>},
+            {k_multinomial_binomial<true, 0>, k_multinomial_binomial<true, 1>, k_multinomial_binomial<true, 2>}};
+        int32_t* group_counts = nullptr;
+        if (G > 1) {
+            group_counts = static_cast<int32_t*>(scratch(st, 24, sizeof(int32_t) * (size_t)items * G));
+            if (!group_counts) return QPB_ERR_NOMEM;
+        }
+        // Every thread walks its chain from start to end, so a launch that needs one block more than fits takes twice
+        // as long: pick the largest block size whose grid is resident at once, else 128 and a grid-stride loop
+        static int occ[2][3][3] = {};  // resident blocks per SM for 128 / 96 / 64 threads
         const int cand[3] = {128, 96, 64};
-        int threads = option(QPB_OPT_SAMPLER_THREADS) > 0 ? option(QPB_OPT_SAMPLER_THREADS) : 0;
-        if (threads == 0) {
-            threads = 128;
-            for (int c = 0; c < 3; ++c) {
-                if (occ[prefilter][gi][c] == 0) {
-                    int nb = 0;
-                    QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, cand[c], 0));
-                    occ[prefilter][gi][c] = nb > 0 ? nb : 1;
-                }
-                if ((items * G + cand[c] - 1) / cand[c] <= (long)num_sms() * occ[prefilter][gi][c]) {
-                    threads = cand[c];
-                    break;
+        for (int mode = (G > 1 ? 1 : 0); mode <= (G > 1 ? 2 : 0); ++mode) {
+            kern_t kern = table[prefilter][mode];
+            const long work = mode == 2 ? items * G : items;
+            int threads = option(QPB_OPT_SAMPLER_THREADS) > 0 ? option(QPB_OPT_SAMPLER_THREADS) : 0;
+            if (threads == 0) {
+                threads = 128;
+                for (int c = 0; c < 3; ++c) {
+                    if (occ[prefilter][mode][c] == 0) {
+                        int nb = 0;
+                        QPB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, cand[c], 0));
+                        occ[prefilter][mode][c] = nb > 0 ? nb : 1;
+                    }
+                    if ((work + cand[c] - 1) / cand[c] <= (long)num_sms() * occ[prefilter][mode][c]) {
+                        threads = cand[c];
+                        break;
+                    }
                 }
             }
+            long blocks = (work + threads - 1) / threads;
+            const long cap = (long)num_sms() * 16;
+            if (blocks > cap) blocks = cap;
+            kern<<<(int)blocks, threads, 0, st>>>(B, P, O, G, p, p_batched, shots, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                  offset, counts, group_counts, every);
+            QPB_LAUNCHED("k_multinomial_binomial");
         }
-        long blocks = (items * G + threads - 1) / threads;
-        const long cap = (long)num_sms() * 16;
-        if (blocks > cap) blocks = cap;
-        kern<<<(int)blocks, threads, 0, st>>>(B, P, O, p, p_batched, shots, (uint32_t)seed, (uint32_t)(seed >> 32), offset,
-                                              counts, every);
-        QPB_LAUNCHED("k_multinomial_binomial");
         return QPB_OK;
     }
     uint2* tables = nullptr;

@@ -28,6 +28,11 @@ def _pop_hidden_keys(kwargs):
     return {k: v for k, v in kwargs.items() if k not in ("self", "tmg") and not k.startswith("__")}
 
 
+_DEFAULT_LEVELS = np.linspace(1e-3, 1 - 1e-3, 1000)  # ConfidenceInterval.__call__'s default (interval.py:41-42)
+_DEFAULT_LEVELS.setflags(write=False)
+_NO_LEVELS = np.zeros(0)
+
+
 class ConfidenceInterval(ABC):
     """Functor: interval(conf_levels) -> (distances, conf_levels); `setup` runs lazily on first call."""
 
@@ -47,7 +52,7 @@ class ConfidenceInterval(ABC):
 
     def __call__(self, conf_levels=None):
         if conf_levels is None:
-            conf_levels = np.linspace(1e-3, 1 - 1e-3, 1000)
+            conf_levels = _DEFAULT_LEVELS.copy()
         if not hasattr(self, "cl_to_dist"):
             if self._setup_takes_levels:
                 self.setup(conf_levels=conf_levels)  # the levels travel with the set-up call
@@ -151,9 +156,14 @@ class BootstrapStateInterval(ConfidenceInterval):
         if kind is not None and hi > lo and engine.FUSED_INTERVAL:
             # built-in distance: ONE library call with host inputs and outputs (qpb_bootstrap_state_interval) runs this
             # rank's shard -- upload, probabilities, bootstrap, shard sort and, on one GPU, the quantiles as well
-            levels = np.linspace(1e-3, 1 - 1e-3, 1000) if conf_levels is None else np.asarray(conf_levels, dtype=np.float64)
-            if size > 1 or np.any(levels < 0) or np.any(levels > 1):
-                levels = np.zeros(0)  # several GPUs: after the gather; bad levels: cl_to_dist raises interp1d's error
+            if size > 1:
+                levels = _NO_LEVELS    # several GPUs: the quantiles follow the gather
+            elif conf_levels is None:
+                levels = _DEFAULT_LEVELS
+            else:
+                levels = np.asarray(conf_levels, dtype=np.float64)
+                if levels.size and (levels.min() < 0 or levels.max() > 1):
+                    levels = _NO_LEVELS  # cl_to_dist raises interp1d's error when it is called
             q, dist, self._iters_dev = engine.bootstrap_interval(
                 plan, self.state.bloch, self.state.matrix, hi - lo, seed, lo, method, self.physical, self.init,
                 self.max_iter, self.tol, kind, levels)

@@ -76,10 +76,11 @@ def test_probabilities_match_reference(qp, golden, case):
     assert np.abs(p - g["probs"]).max() < 1e-14
 
 
-@pytest.fixture(params=["binomial", "alias", "binomial-4-lanes", "binomial-8-lanes"])
+@pytest.fixture(params=["binomial", "alias", "binomial-1-group", "binomial-3-groups", "binomial-8-groups"])
 def sampler_kind(request):
-    """Both multinomial kernels -- and the conditional-binomial one with its outcomes split over 4 / 8 lanes per
-    item (a binary tree of group splits first: SAMPLER_LANES) -- are held to the same distributional tests."""
+    """Both multinomial kernels -- and the conditional-binomial one as a single chain and with its outcomes in 3 / 8
+    groups (SAMPLER_LANES; the default picks the number of groups from the number of outcomes: a pass that splits the
+    shots between the groups, then a chain per group) -- are held to the same distributional tests."""
     from quantpy_b200 import _native as nt
 
     kind, _, lanes = request.param.partition("-")

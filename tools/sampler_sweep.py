@@ -30,7 +30,7 @@ def run(B, reps=10):
     return min(ms), float(np.median(ms)), int((c.flatten().long() * w).sum().item())
 with nt.option("SAMPLER", nt.SAMPLERS["binomial"]):
     for B in Bs:
-        for nopre, every, threads in itertools.product([1, 0], [1, 2, 3], [0, 128, 96, 64, 32]):
-            with nt.option("SAMPLER_NO_PREFILTER", nopre), nt.option("SAMPLER_EXACT_EVERY", every), nt.option("SAMPLER_THREADS", threads):
+        for groups, nopre, every, threads in itertools.product([1, 2, 3, 4, 6, 9, 12], [0], [1, 2], [0, 128, 64]):
+            with nt.option("SAMPLER_LANES", groups), nt.option("SAMPLER_NO_PREFILTER", nopre), nt.option("SAMPLER_EXACT_EVERY", every), nt.option("SAMPLER_THREADS", threads):
                 t, med, h = run(B)
-            print(f"n {n} B {B} prefilter {1 - nopre} exact_every {every} threads {threads or 'auto'}: {t:.4f} ms (median {med:.4f}) checksum {h}", flush=True)
+            print(f"n {n} B {B} groups {groups} prefilter {1 - nopre} exact_every {every} threads {threads or 'auto'}: {t:.4f} ms (median {med:.4f}) checksum {h}", flush=True)
