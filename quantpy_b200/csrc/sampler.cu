@@ -193,13 +193,13 @@ __device__ __forceinline__ float stirling_tail_f(double k) {  // float32 copy fo
 }
 
 // Binomial(n, p) for 0 < p <= 0.5 and n*p < 10: sequential search from 0 (BINV).
-__device__ long binomial_inversion(long n, double p, PhiloxStream& rng) {
+__device__ int binomial_inversion(int n, double p, PhiloxStream& rng) {
     const double q = 1.0 - p;
-    const double s = p / q, a = (double)(n + 1) * s;
+    const double s = p / q, a = ((double)n + 1.0) * s;
     const double r0 = exp((double)n * log(q));
     for (;;) {
         double u = rng.next(), r = r0;
-        long x = 0;
+        int x = 0;
         bool ok = true;
         while (u > r) {
             u -= r;
@@ -218,7 +218,7 @@ __device__ long binomial_inversion(long n, double p, PhiloxStream& rng) {
 // J. Stat. Comput. Simul. 46 (1993)); valid for p <= 0.5 and n*p >= 10.
 struct Btrs {
     double a, b, c, vr, alpha, r, m, n;
-    __device__ __forceinline__ void setup(long n_, double p) {
+    __device__ __forceinline__ void setup(int n_, double p) {
         // reciprocals and the square root from the hardware seeds + Newton steps (1 ulp): the constants only
         // have to be consistent between proposal and acceptance test, and IEEE div / sqrt were a third of the
         // instructions of a variate
@@ -236,12 +236,12 @@ struct Btrs {
     }
     // One proposal (u, v from the lane's stream): >= 0 accepted inside the squeeze (~86 % of proposals), -1 rejected
     // (outside the support), -2 undecided: the candidate kd needs the exact test below.
-    __device__ __forceinline__ long propose(PhiloxStream& rng, double& kd, double& v, double& us) const {
+    __device__ __forceinline__ int propose(PhiloxStream& rng, double& kd, double& v, double& us) const {
         const double u = rng.next() - 0.5;
         v = rng.next();
         us = 0.5 - fabs(u);
         kd = floor((2.0 * a * fast_recip(us) + b) * u + c);
-        if (us >= 0.07 && v <= vr) return (long)kd;
+        if (us >= 0.07 && v <= vr) return (int)kd;
         if (kd < 0.0 || kd > n) return -1;
         return -2;
     }
@@ -333,7 +333,7 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, int 
             return s;
         };
         int o_begin = 0, o_end = MODE == 1 ? G : O;
-        long left = shots.n[m];
+        int left = shots.n[m];  // 32-bit: the shot numbers are int32 (conversions to and from double are single instructions)
         double mass = 1.0, po = 0.0;
         int32_t* out = MODE == 1 ? group_counts + item * G : counts + item * O;
         if (MODE == 2) {
@@ -364,7 +364,7 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, int 
             ++trip;
             if (!ready) {  // set up the lane's next binomial, then fall through to its first proposal
                 po = prob(o);
-                long c = -1;
+                int c = -1;
                 if (left <= 0 || !(po > 0.0)) {
                     c = 0;
                 } else {
@@ -373,7 +373,7 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, int 
                     const double r = flip ? 1.0 - cond : cond;
                     if (!(r > 0.0)) c = flip ? left : 0;
                     else if ((double)left * r < 10.0) {
-                        const long y = binomial_inversion(left, r, rng);
+                        const int y = binomial_inversion(left, r, rng);
                         c = flip ? left - y : y;
                     } else {
                         st.setup(left, r);
@@ -387,19 +387,19 @@ __global__ void __maxnreg__(88) k_multinomial_binomial(int B, int P, int O, int 
                     ++o;
                 }
             }
-            long y = -1;
+            int y = -1;
             if (ready && !pending) {
                 y = st.propose(rng, cand, cv, cus);
                 pending = y == -2;
             }
-            if (pending && trip % exact_every == 0) {
+            if (pending && (trip & (exact_every - 1)) == 0) {  // exact_every is a power of two
                 pending = false;
                 int verdict = PREFILTER ? st.accept_quick(cand, cv, cus) : -1;
                 if (verdict < 0) verdict = st.accept_exact(cand, cv, cus) ? 1 : 0;  // a few per 10^4 candidates
-                y = verdict ? (long)cand : -1;
+                y = verdict ? (int)cand : -1;
             }
             if (y >= 0) {
-                const long c = flip ? left - y : y;
+                const int c = flip ? left - y : y;
                 out[o] = (int32_t)c;
                 left -= c;
                 mass -= po;
@@ -449,6 +449,7 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
         QPB_REQUIRE(G >= 1 && G <= 64, "SAMPLER_LANES (groups per item) must be in 1..64");
         while (G > 1 && (G - 1) * ((O + G - 1) / G) >= O - 1) --G;  // the last group keeps two outcomes of its own
         if (every == 0) every = G > 1 ? 1 : kExactEvery;  // short chains: waiting for an even trip costs more than it saves
+        while (every & (every - 1)) every &= every - 1;   // the kernel tests trip & (every - 1)
         typedef void (*kern_t)(int, int, int, int, const double*, int, ShotVec, uint32_t, uint32_t, uint64_t, int32_t*,
                                int32_t*, int);
         static const kern_t table[2][3] = {
