@@ -340,19 +340,28 @@ __device__ __forceinline__ void iterate(const PauliParams& pp, const double (&h)
 __device__ __forceinline__ double normalise_step(const double (&hn)[16], double (&h)[16]) {
     const double tr = dadd(dadd(hn[0], hn[5]), dadd(hn[10], hn[15]));
     const double inv = fast_recip(tr);
-    double p[8];
+    double dd[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int e0 = 2 * j, e1 = 2 * j + 1;
-        const double x0 = dmul(hn[e0], inv), x1 = dmul(hn[e1], inv);
-        const double d0 = dsub(x0, h[e0]), d1 = dsub(x1, h[e1]);
-        // weights 1 (diagonal) or 2 (the pair (a,b), (b,a)): a product with 1.0 is the operand itself
-        const double w0 = (e0 / 4 == e0 % 4) ? d0 : dmul(2.0, d0), w1 = (e1 / 4 == e1 % 4) ? d1 : dmul(2.0, d1);
-        p[j] = dfma(w1, d1, dmul(w0, d0));
-        h[e0] = x0;
-        h[e1] = x1;
+    for (int e = 0; e < 16; ++e) {
+        const double x = dmul(hn[e], inv);
+        dd[e] = dsub(x, h[e]);
+        h[e] = x;
     }
-    return dadd(dadd(dadd(p[0], p[1]), dadd(p[2], p[3])), dadd(dadd(p[4], p[5]), dadd(p[6], p[7])));
+    // ||h' - h||_F^2 = sum_e m_e d_e^2, m = 1 on the diagonal and 2 for a pair (a,b), (b,a): four rows of four entries,
+    // each a length-4 FMA chain of (m d) * d in index order, then the four row sums in order -- the arithmetic of the
+    // two DMMAs that compute it in the warp-per-sample mapping
+    double row[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        Chain c;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e = 4 * r + k;
+            c.term((e / 4 == e % 4) ? dd[e] : dmul(2.0, dd[e]), dd[e]);  // a product with 1.0 is the operand itself
+        }
+        row[r] = c.acc;
+    }
+    return dadd(dadd(dadd(row[0], row[1]), row[2]), row[3]);
 }
 }  // namespace single
 
@@ -381,7 +390,7 @@ __device__ __forceinline__ void herm2_component(int r2, int c2, int part, int& c
     }
 }
 
-template <bool UG>
+template <bool UG, bool TRACE>
 __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __restrict__ wb, const int lane) {
     const unsigned full = 0xffffffffu;
     // ---- per-lane constants of the graph ---------------------------------------------------------
@@ -406,8 +415,10 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
             }
         }
     }
-    const double m_even = ((i16 & ~1) / 4 == (i16 & ~1) % 4) ? 1.0 : 2.0;
-    const double m_odd = ((i16 | 1) / 4 == (i16 | 1) % 4) ? 1.0 : 2.0;
+    // step norm: entry i16 weighs 1 (diagonal) or 2; after the first DMMA row sum r sits in lane 4 r + r / 2
+    const double m_self = (i16 / 4 == i16 % 4) ? 1.0 : 2.0;
+    const int row_src = 4 * (lane & 3) + ((lane & 3) >> 1);
+    const bool row_odd = (lane >> 2) & 1;
     // B fragment of the first product: [Pr | Pi][k][n], k = lane & 3, n = lane >> 2
     int bo = ZERO;
     unsigned bneg = 0;
@@ -511,7 +522,10 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
     const double tol2 = a.tol * a.tol;
     const int K = pp.K;
     if (lane == 0) wb[ZERO] = 0.0;
-    long long* const tr_w = a.trace ? a.trace + 16 * ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : nullptr;
+    // profiling stamps and counters exist in the TRACE instantiation only (tools/pauli2_trace.py): six 64-bit counters in
+    // the loops cost the thread-per-sample mapping registers it does not have
+    long long* const tr_w = (TRACE && a.trace) ? a.trace + 16 * ((size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) : nullptr;
+    long long* const trace_s = TRACE ? a.trace_s : nullptr;
     long long tr_samples = 0, tr_its = 0, tr_wait = 0;
     if (tr_w && lane == 0) tr_w[8] = (long long)globaltimer_ns();
 
@@ -558,7 +572,7 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
         it = __shfl_sync(full, it, 0);
         const int tr_it0 = it;
         const long long tr_t0 = tr_w ? (long long)globaltimer_ns() : 0;
-        if (a.trace_s && lane == 0) a.trace_s[4 * b + (from_park ? 2 : 0)] = tr_t0;
+        if (trace_s && lane == 0) trace_s[4 * b + (from_park ? 2 : 0)] = tr_t0;
         from_park = __shfl_sync(full, from_park, 0);
         // ---- frequencies by slot, start state -----------------------------------------------------------
         __syncwarp();
@@ -609,7 +623,11 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
                 const double bfrag = dmul(flip(wb[bo], bneg), inv);
                 const double xe = dmul(wb[HN + i16], inv);
                 const double dstep = dsub(xe, hprev);
-                const double dpart = __shfl_xor_sync(full, dstep, 1);
+                // step norm on the tensor pipe: rows of A = (m d) in fours, columns of B = d in fours, so that the
+                // diagonal of the product holds the four row sums as FMA chains in index order ...
+                double sn0 = 0.0, sn1 = 0.0;
+                dmma(sn0, sn1, dmul(m_self, dstep), dstep);
+                const double row_sum = row_odd ? sn1 : sn0;  // D[r][r] in lane 4 r + r / 2: element r % 2
                 hprev = xe;
                 it += first ? 0 : 1;
                 __syncwarp();
@@ -629,12 +647,8 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
                     wb[W + lane] = w0;
                     if (lane < 4) wb[W + 32 + lane] = w1;
                 }
-                double pstep;
-                {
-                    const double de = (lane & 1) ? dpart : dstep, dodd = (lane & 1) ? dstep : dpart;
-                    pstep = dfma(dmul(m_odd, dodd), dodd, dmul(dmul(m_even, de), de));
-                }
-                const double pstep2 = __shfl_xor_sync(full, pstep, 2);
+                // ... and a second product with a matrix of ones adds the four row sums in order, in every lane
+                const double row_k = __shfl_sync(full, row_sum, row_src);
                 __syncwarp();
                 // -- P2: qubit-2 map ----------------------------------------------------------------------------
                 {
@@ -646,8 +660,8 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
                     const double nv = n_c < 2 ? dadd(y0, dd) : dd;
                     if (lane < 24) wb[N + lane] = nv;
                 }
-                pstep = dadd(pstep, pstep2);
-                const double pstep4 = __shfl_xor_sync(full, pstep, 4);
+                double pstep = 0.0, pstep_dup = 0.0;
+                dmma(pstep, pstep_dup, row_k, 1.0);
                 __syncwarp();
                 // -- P3: qubit-1 map -> fragment of R; first product ------------------------------------------
                 double val;
@@ -658,8 +672,6 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
                     const double n6 = flip(wb[ro[6]], (rneg >> 6) & 1u), n7 = flip(wb[ro[7]], (rneg >> 7) & 1u);
                     val = dadd(dadd(dadd(dadd(n0, n1), dadd(n2, n3)), dadd(n4, n5)), dadd(n6, n7));
                 }
-                pstep = dadd(pstep, pstep4);
-                pstep = dadd(pstep, __shfl_xor_sync(full, pstep, 8));
                 del = first ? 1e300 : pstep;
                 // every lane holds the same bits of del and it (lanes 16-31 mirror lanes 0-15): a uniform branch
                 if (del < tol2 || it >= a.max_iter) break;
@@ -709,7 +721,7 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
                 if (a.iters) a.iters[b] = it;
                 if (!a.direct) atomicAdd(&a.ctrl[3], 1u);
             }
-            if (a.trace_s && lane == 0) a.trace_s[4 * b + 3] = (long long)globaltimer_ns();
+            if (trace_s && lane == 0) trace_s[4 * b + 3] = (long long)globaltimer_ns();
             tr_samples += 1;
             tr_its += it - tr_it0;
             if (tr_w) tr_wait += (long long)globaltimer_ns() - tr_t0;  // busy time, in fact
@@ -737,7 +749,7 @@ __device__ __forceinline__ void load_frequencies(const PauliParams& pp, const in
         if (k < K) fcol[pp.slot_of_col[k] * kPauliThreadsSingle] = freq((double)cc[k]);
 }
 
-template <bool UG>  // all used slots share one 1e-10/c: fold it into S_00 instead of 36 additions
+template <bool UG, bool TRACE>  // UG: all used slots share one 1e-10/c: fold it into S_00 instead of 36 additions
 __global__ void __launch_bounds__(384, 1)
 k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__ Pauli2Args a) {
     constexpr int D = 16;
@@ -758,7 +770,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
         __syncthreads();
     }
     if (warp >= a.single_warps) {
-        wmode::worker<UG>(pp, a, wbase, lane);
+        wmode::worker<UG, TRACE>(pp, a, wbase, lane);
         return;
     }
     const int K = pp.K;
@@ -772,7 +784,8 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
     bool plateau = false;
     unsigned tick = 0;
     bool dissolved = false;  // this warp pushed its samples onto the packing stack
-    long long* const tr_s = a.trace ? a.trace + 16 * ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) : nullptr;
+    long long* const tr_s = (TRACE && a.trace) ? a.trace + 16 * ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) : nullptr;
+    long long* const trace_s = TRACE ? a.trace_s : nullptr;
     long long tr_wi = 0, tr_li = 0, tr_wi_tail = 0, tr_li_tail = 0, tr_parked = 0, tr_adopted = 0;
     bool tr_seen_drain = false;
     if (tr_s && lane == 0) tr_s[0] = (long long)globaltimer_ns();
@@ -800,7 +813,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
             }
             if (a.hs_dist) a.hs_dist[ob] = hs_distance_packed(h, a.hs_ref);
             if (a.iters) a.iters[ob] = it;
-            if (a.trace_s) a.trace_s[4 * ob + 3] = (long long)globaltimer_ns();
+            if (trace_s) trace_s[4 * ob + 3] = (long long)globaltimer_ns();
             b = -1;
         }
         if (hand_over && lane == 0) atomicAdd(&a.ctrl[3], (unsigned)__popc(wbm));
@@ -829,7 +842,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
                         if (nb > a.park_q2)
                             my_age = max(a.park_age_end, my_age - (int)((float)(nb - a.park_q2) * a.park_age_slope2));
                     }
-                    if (a.trace_s) a.trace_s[4 * b] = (long long)globaltimer_ns();
+                    if (trace_s) trace_s[4 * b] = (long long)globaltimer_ns();
                     it = 0;
                     plateau = false;
                     load_frequencies(pp, a.counts + b * K, K, fs + tid);
@@ -965,7 +978,7 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
                 for (int e = 0; e < 8; ++e) __stcg(dst + e, make_double2(h[2 * e], h[2 * e + 1]));
                 a.park_b[slot] = b;
                 a.park_it[slot] = it;
-                if (a.trace_s) a.trace_s[4 * b + 1] = (long long)globaltimer_ns();
+                if (trace_s) trace_s[4 * b + 1] = (long long)globaltimer_ns();
                 __threadfence();
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.park_ready + slot), "r"(a.epoch) : "memory");
                 b = -1;
@@ -1072,15 +1085,15 @@ k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__
         tr_s[14] = tr_adopted;
     }
     // out of single-lane work: serve the hand-over list until every sample of the launch is finished
-    if (hand_over) wmode::worker<UG>(pp, a, wbase, lane);
+    if (hand_over) wmode::worker<UG, TRACE>(pp, a, wbase, lane);
 }
 
 // Warp-per-sample workers only (small batches): few registers, so 32 warps per SM hide each other's latency.
-template <bool UG, int THREADS>
+template <bool UG, int THREADS, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_mle_rrr_pauli2_w(const __grid_constant__ PauliParams pp, const __grid_constant__ Pauli2Args a) {
     extern __shared__ __align__(16) double sm[];
-    wmode::worker<UG>(pp, a, sm + (size_t)(threadIdx.x >> 5) * wmode::SIZE, threadIdx.x & 31);
+    wmode::worker<UG, TRACE>(pp, a, sm + (size_t)(threadIdx.x >> 5) * wmode::SIZE, threadIdx.x & 31);
 }
 
 // Recognise a two-qubit Pauli-axis POVM from the Bloch-basis table A [K][16] (host copy).
@@ -1290,11 +1303,20 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
     if (a.epoch == 0) a.epoch = epoch_counter.fetch_add(1);
 
     const size_t smem = sizeof(double) * ((size_t)(threads / 32) * wmode::SIZE + (a.direct ? 0 : 36 * kPauliThreadsSingle + kPoolWords * 32 + 8));
-    auto pk = pp.uniform ? k_mle_rrr_pauli2<true> : k_mle_rrr_pauli2<false>;
+    const bool tr = a.trace != nullptr;
+    auto pk = pp.uniform ? (tr ? k_mle_rrr_pauli2<true, true> : k_mle_rrr_pauli2<true, false>)
+                         : (tr ? k_mle_rrr_pauli2<false, true> : k_mle_rrr_pauli2<false, false>);
     if (a.direct) {
-        if (threads <= 512) pk = pp.uniform ? k_mle_rrr_pauli2_w<true, 512> : k_mle_rrr_pauli2_w<false, 512>;
-        else if (threads <= 768) pk = pp.uniform ? k_mle_rrr_pauli2_w<true, 768> : k_mle_rrr_pauli2_w<false, 768>;
-        else pk = pp.uniform ? k_mle_rrr_pauli2_w<true, 1024> : k_mle_rrr_pauli2_w<false, 1024>;
+        const bool u = pp.uniform;
+        if (threads <= 512)
+            pk = u ? (tr ? k_mle_rrr_pauli2_w<true, 512, true> : k_mle_rrr_pauli2_w<true, 512, false>)
+                   : (tr ? k_mle_rrr_pauli2_w<false, 512, true> : k_mle_rrr_pauli2_w<false, 512, false>);
+        else if (threads <= 768)
+            pk = u ? (tr ? k_mle_rrr_pauli2_w<true, 768, true> : k_mle_rrr_pauli2_w<true, 768, false>)
+                   : (tr ? k_mle_rrr_pauli2_w<false, 768, true> : k_mle_rrr_pauli2_w<false, 768, false>);
+        else
+            pk = u ? (tr ? k_mle_rrr_pauli2_w<true, 1024, true> : k_mle_rrr_pauli2_w<true, 1024, false>)
+                   : (tr ? k_mle_rrr_pauli2_w<false, 1024, true> : k_mle_rrr_pauli2_w<false, 1024, false>);
     }
     QPB_CUDA(cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     pk<<<blocks, threads, smem, st>>>(pp, a);
