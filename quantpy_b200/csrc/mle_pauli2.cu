@@ -1236,7 +1236,7 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
             // (tools/pauli2_sweep_n.py: below half a wave of lanes a late general age with an early start for the first
             // queue positions beats the early general age: 12 500 samples 0.788 -> 0.710 ms per step)
             const bool half_wave = (long long)B * 2 <= lanes;
-            const int age = (long long)B * 2 <= lanes * 3 ? 300 : 500;
+            const int age = half_wave ? 300 : ((long long)B * 2 <= lanes * 3 ? 350 : 500);
             a.park_age = option(QPB_OPT_MLE_PARK_AGE) > 0 ? option(QPB_OPT_MLE_PARK_AGE) : age;
             {
                 // measured on B200 (tools/pauli2_sweep_h.py): while most of the batch starts in the first wave of
@@ -1245,7 +1245,9 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
                 const int lo = option(QPB_OPT_MLE_PARK_AGE_LO), pct = option(QPB_OPT_MLE_PARK_AGE_PCT);
                 a.park_age_lo = lo > 0 ? lo : (lo < 0 ? a.park_age : (half_wave ? 100 : (few_waves ? 250 : 350)));
                 if (a.park_age_lo > a.park_age) a.park_age_lo = a.park_age;
-                const double frac = (pct > 0 ? pct : (few_waves ? 50 : 10)) / 100.0;
+                // (tools/pauli2_sweep_o.py, 5e4 samples: age 350 from 250 over the first 10 % and no demand-driven tail
+                // 1.16 -> 1.07 ms per step)
+                const double frac = (pct > 0 ? pct : (half_wave ? 50 : 10)) / 100.0;
                 a.park_age_slope = (float)((a.park_age - a.park_age_lo) / (frac * (double)B));
                 const int end = option(QPB_OPT_MLE_PARK_AGE_END), pct2 = option(QPB_OPT_MLE_PARK_AGE_PCT2);
                 a.park_q2 = (int)(lanes < B ? lanes : B);
@@ -1257,7 +1259,7 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
             a.park_live = option(QPB_OPT_MLE_PARK_LIVE) > 0 ? option(QPB_OPT_MLE_PARK_LIVE) : (half_wave ? 20 : 5);
             if (a.single_warps < max_sw || a.single_warps + w_warps > kPauliWarps) w_warps = kPauliWarps - a.single_warps;
             const int poll = option(QPB_OPT_MLE_TAIL_POLL);
-            a.tail_poll = poll < 0 ? 0 : (poll == 0 ? 4 : poll);
+            a.tail_poll = poll < 0 ? 0 : (poll == 0 ? (((long long)B * 2 <= lanes * 3 && !half_wave) ? 0 : 4) : poll);
             while (a.tail_poll & (a.tail_poll - 1)) a.tail_poll &= a.tail_poll - 1;  // power of two
             a.tail_age = option(QPB_OPT_MLE_TAIL_AGE) > 0 ? option(QPB_OPT_MLE_TAIL_AGE) : 150;
             const int ad = option(QPB_OPT_MLE_ADOPT);
