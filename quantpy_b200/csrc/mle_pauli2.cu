@@ -301,37 +301,46 @@ __device__ __forceinline__ void iterate(const PauliParams& pp, const double (&h)
             Pr[a][b] = a <= b ? h[a * 4 + b] : h[b * 4 + a];
             Pi[a][b] = a == b ? 0.0 : (a < b ? h[b * 4 + a] : -h[a * 4 + b]);
         }
-    // hn = (R P) R, upper triangle; row by row so that only one row of S = R P is live
+    // hn = (R P) R, upper triangle; row by row so that only one row of S = R P is live.  Every real and every imaginary
+    // part is ONE chain: Re (X Y)[a][b] = sum_k Xr Yr, then sum_k (-Xi) Yi;  Im = sum_k Xr Yi, then sum_k Xi Yr -- the
+    // order in which two DMMAs accumulating into one fragment produce them in the warp-per-sample mapping
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         double Sr[4], Si[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            Chain rr, ii, ri, ir;
+            Chain re, im;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                rr.term(Rr[a][k], Pr[k][b]);
-                if (a != k && k != b) ii.term(Ri[a][k], Pi[k][b]);
-                if (k != b) ri.term(Rr[a][k], Pi[k][b]);
-                if (a != k) ir.term(Ri[a][k], Pr[k][b]);
-            }
-            Sr[b] = dsub(rr.acc, ii.acc);
-            Si[b] = dadd(ri.acc, ir.acc);
+            for (int k = 0; k < 4; ++k) re.term(Rr[a][k], Pr[k][b]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (a != k && k != b) re.term(-Ri[a][k], Pi[k][b]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k != b) im.term(Rr[a][k], Pi[k][b]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (a != k) im.term(Ri[a][k], Pr[k][b]);
+            Sr[b] = re.acc;
+            Si[b] = im.acc;
         }
 #pragma unroll
         for (int b = a; b < 4; ++b) {
-            Chain rr, ii, ri, ir;
+            Chain re, im;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                rr.term(Sr[k], Rr[k][b]);
-                if (k != b) ii.term(Si[k], Ri[k][b]);
-                if (a != b) {
-                    if (k != b) ri.term(Sr[k], Ri[k][b]);
-                    ir.term(Si[k], Rr[k][b]);
-                }
+            for (int k = 0; k < 4; ++k) re.term(Sr[k], Rr[k][b]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (k != b) re.term(-Si[k], Ri[k][b]);
+            hn[a * 4 + b] = re.acc;
+            if (a != b) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k != b) im.term(Sr[k], Ri[k][b]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) im.term(Si[k], Rr[k][b]);
+                hn[b * 4 + a] = im.acc;
             }
-            hn[a * 4 + b] = dsub(rr.acc, ii.acc);
-            if (a != b) hn[b * 4 + a] = dadd(ri.acc, ir.acc);
         }
     }
 }
@@ -517,7 +526,6 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
         else if (ra < rb) out_src = rb * 4 + ra;
         else { out_src = ra * 4 + rb; out_neg = 1; }
     }
-    const unsigned pair_neg = (lane & 2) ? 0u : 1u;  // the product pairs: lanes with bit 1 clear hold a difference
     const unsigned hi_half = lane < 16 ? 0u : 1u;   // second product: the imaginary half takes -R
     const double tol2 = a.tol * a.tol;
     const int K = pp.K;
@@ -676,27 +684,29 @@ __device__ void worker(const PauliParams& pp, const Pauli2Args& a, double* __res
                 // every lane holds the same bits of del and it (lanes 16-31 mirror lanes 0-15): a uniform branch
                 if (del < tol2 || it >= a.max_iter) break;
                 first = false;
+                // S = R P: [Rr; Ri] x [Pr | Pi], then [-Ri; -Rr] x [Pi | -Pr] into the same fragment: rows 0-3 hold
+                // Re S = Rr Pr - Ri Pi in columns 0-3 and Im S = Rr Pi + Ri Pr in columns 4-7, each as ONE chain
+                const double valx = flip(__shfl_xor_sync(full, val, 16), 1u);  // lanes < 16: -Ri, the others: -Rr
                 {
+                    const double bfragx = flip(__shfl_xor_sync(full, bfrag, 16), hi_half);
                     double d0 = 0.0, d1 = 0.0;
                     dmma(d0, d1, val, bfrag);
-                    const double p0 = __shfl_xor_sync(full, d0, 18), p1 = __shfl_xor_sync(full, d1, 18);
-                    // lanes with bit 1 clear subtract: d - p = d + (-p) bit for bit, the sign flips on the integer pipe
-                    const double r0 = dadd(d0, flip(p0, pair_neg));
-                    const double r1 = dadd(d1, flip(p1, pair_neg));
-                    if (lane < 16) *reinterpret_cast<double2*>(wb + xo) = make_double2(r0, r1);
+                    dmma(d0, d1, valx, bfragx);
+                    if (lane < 16) *reinterpret_cast<double2*>(wb + xo) = make_double2(d0, d1);
                 }
                 __syncwarp();
                 // -- P4: second product -> unnormalised new state ---------------------------------------------
+                // T = S R: [Sr; Si] x [Rr | Ri], then [-Si; -Sr] x [Ri | -Rr]; in the B layout (k = column of R, by
+                // Hermiticity) the second right operand is valx itself
                 {
                     const double a2 = wb[X + lane];
+                    const double a2x = flip(wb[X + (lane ^ 16)], 1u);
                     const double b2 = flip(val, hi_half);
                     double d0 = 0.0, d1 = 0.0;
                     dmma(d0, d1, a2, b2);
-                    const double p0 = __shfl_xor_sync(full, d0, 18), p1 = __shfl_xor_sync(full, d1, 18);
-                    const double r0 = dadd(d0, flip(p0, pair_neg));
-                    const double r1 = dadd(d1, flip(p1, pair_neg));
-                    if (ho0 >= 0) wb[ho0] = r0;
-                    if (ho1 >= 0) wb[ho1] = r1;
+                    dmma(d0, d1, a2x, valx);
+                    if (ho0 >= 0) wb[ho0] = d0;
+                    if (ho1 >= 0) wb[ho1] = d1;
                 }
                 __syncwarp();
             }
