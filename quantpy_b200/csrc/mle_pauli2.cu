@@ -138,6 +138,10 @@ struct Pauli2Args {
 constexpr int kPauliThreadsSingle = 384;  // most thread-per-sample lanes per CTA (12 warps: 3 per scheduler) = stride of the
                                           // frequency columns; the launch decides how many of the 12 warps start that way
 constexpr int kPauliWarps = kPauliThreadsSingle / 32;
+#ifndef PAULI_CTA_WARPS
+#define PAULI_CTA_WARPS 12
+#endif
+constexpr int kPauliCtaWarps = PAULI_CTA_WARPS;  // warps of a CTA (thread-per-sample + W workers): sets the register budget
 constexpr int kCxTop = kPauliWarps, kCxLock = kPauliWarps + 1;  // packing stack: entries, lock (after the live[] words)
 constexpr int kPoolWords = 54;             // a sample on the packing stack: 16 state + 36 frequencies + index + age
 
@@ -760,7 +764,7 @@ __device__ __forceinline__ void load_frequencies(const PauliParams& pp, const in
 }
 
 template <bool UG, bool TRACE>  // UG: all used slots share one 1e-10/c: fold it into S_00 instead of 36 additions
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(32 * kPauliCtaWarps, 1)
 k_mle_rrr_pauli2(const __grid_constant__ PauliParams pp, const __grid_constant__ Pauli2Args a) {
     constexpr int D = 16;
     extern __shared__ __align__(16) double sm[];
@@ -1187,9 +1191,9 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
     // 1.31 ms thread-per-sample; from B ~ 5000 on the hybrid wins)
     bool direct = lanes_opt == 32 || (lanes_opt == 0 && !option(QPB_OPT_NO_TAIL_MERGE) && (long long)B <= (long long)sms * 24);
     int w_warps = option(QPB_OPT_MLE_W_WARPS);
-    if (w_warps == 0) w_warps = 4;
+    if (w_warps == 0) w_warps = kPauliCtaWarps - 8;
     if (w_warps < 0) w_warps = 0;
-    if (w_warps > 4) w_warps = 4;
+    if (w_warps > kPauliCtaWarps - 8) w_warps = kPauliCtaWarps - 8;
     int threads, blocks;
     if (direct) {
         a.single_warps = 0;
@@ -1267,7 +1271,7 @@ int launch_mle_pauli2(const qpb_state_plan* plan, int B, const int32_t* counts, 
                 a.park_age_slope2 = (float)((a.park_age - a.park_age_end) / span);
             }
             a.park_live = option(QPB_OPT_MLE_PARK_LIVE) > 0 ? option(QPB_OPT_MLE_PARK_LIVE) : (half_wave ? 20 : 5);
-            if (a.single_warps < max_sw || a.single_warps + w_warps > kPauliWarps) w_warps = kPauliWarps - a.single_warps;
+            if (a.single_warps < max_sw || a.single_warps + w_warps > kPauliCtaWarps) w_warps = kPauliCtaWarps - a.single_warps;
             const int poll = option(QPB_OPT_MLE_TAIL_POLL);
             a.tail_poll = poll < 0 ? 0 : (poll == 0 ? (((long long)B * 2 <= lanes * 3 && !half_wave) ? 0 : 4) : poll);
             while (a.tail_poll & (a.tail_poll - 1)) a.tail_poll &= a.tail_poll - 1;  // power of two
