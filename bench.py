@@ -807,10 +807,12 @@ def strong_record(gpu, cfg, steps, warmup):
         full = step(warmup + i)
         e1.record()
     gpu.barrier()
-    total_s = gpu.max_over_ranks(float(np.sum([e0.elapsed_time(e1) for e0, e1 in evs])) / 1e3)
+    each = [e0.elapsed_time(e1) for e0, e1 in evs]
+    total_s = gpu.max_over_ranks(float(np.sum(each)) / 1e3)
     srt = full.cpu().numpy()
     return {"value": n_total * steps / total_s, "unit": UNIT, "scaling": "strong", "global_resamples": n_total,
             "resamples_per_gpu": hi - lo, "n_gpus": world, "steps": steps, "ms_per_step": 1e3 * total_s / steps,
+            "ms_each": [round(t, 4) for t in each],
             "timed_region": "sampler + lin + MLE + distance on the shard, shard sort, one all-gather, merge of the sorted "
                             "shards; CUDA events, max over ranks, L2 flushed and ranks aligned before every step",
             "sorted_ok": bool(np.all(np.diff(srt) >= 0) and len(srt) == n_total)}
