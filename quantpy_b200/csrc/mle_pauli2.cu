@@ -14,13 +14,15 @@
 // iterate, the iteration count, the result -- does not depend on which of them ran it, nor on when it moved from
 // one to the other:
 //   * thread per sample ("single"): everything in registers, 32 samples per warp.  Cheapest per iteration
-//     (~715 FP64 instructions per sample-iteration), but one iteration is a 2600-cycle serial chain for a lone warp.
+//     (681 FP64 instructions per sample-iteration), but one iteration is a ~2400-cycle serial chain for a lone warp.
 //   * warp per sample ("W"): the 16 Pauli sums, 36 weights, 24 partial operators and 32 fragment entries are one
-//     lane each, exchanged through 1.3 KB of shared memory; the two complex 4x4 products are ONE DMMA
-//     (mma.m8n8k4.f64) each: [Rr;Ri] x [Pr|Pi] gives all four real products, a shfl.xor 18 pairs them up.
+//     lane each, exchanged through 1.3 KB of shared memory; each complex 4x4 product is TWO DMMAs (mma.m8n8k4.f64)
+//     accumulating into one fragment: [Xr;Xi] x [Yr|Yi], then [-Xi;-Xr] x [Yi|-Yr], which leaves Re (X Y) in
+//     columns 0-3 and Im (X Y) in columns 4-7 of rows 0-3, every entry as ONE chain (real terms, then imaginary
+//     terms); the step norm is two more (row sums of (m d) x d on a diagonal, a product with ones for their sum).
 //     DMMA accumulates exactly like an FMA chain in k order (tools/microbench_fp64.cu: 262144 of 262144 outputs
 //     bit-identical), which is what makes the two mappings agree.  ~3x the FP64-pipe cost per iteration, ~5x
-//     shorter chain.
+//     shorter chain; issue-bound (206 instructions per iteration).
 // Iteration counts are heavy-tailed (C2, tol 1e-6: mean 158, p99 578, max 957), so a launch runs the bulk with
 // thread-per-sample warps and moves long-running samples (age >= park_age, or whatever is left in a warp once the
 // queue is empty) through a global hand-over list to W workers: dedicated warps from the start plus every warp
