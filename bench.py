@@ -611,8 +611,15 @@ class StateWorkload:
                        work_note=f"{m['wavefronts_per_draw']} shared-memory wavefronts per categorical draw (ncu, "
                                  "profiles/kernel_models.json), one draw per shot",
                        peak_source="qpb_smem_probe, measured in this run")
+        elif kernels["sampler"] >= kernels["lin_project"]:
+            out.update(kernel="k_multinomial_binomial (two passes)", bound="issue", achieved=None, peak=None, unit=None, frac=None,
+                       work_note="conditional-binomial sampler: bound by fixed-latency dependencies and divergence of the per-lane "
+                                 "state machine (profiles/ncu_r2c_btrs.txt: FP64 pipe 12 %, 17 of 32 lanes active), no pipe roofline")
         else:
-            out.update(bound="smem", achieved=None, peak=peak / 1e9, unit="Gwavefront/s", frac=None)
+            out.update(kernel="lin_project (k_gemm_counts_dmma + k_project_rows)", bound="issue", achieved=None, peak=None,
+                       unit=None, frac=None,
+                       work_note="the register-resident Jacobi projection dominates (profiles/ncu_r1_prof_rows8.txt: issue 61 %, "
+                                 "FP64 pipe 40 %); the DMMA inversion in front of it is reported under dmma_inversion")
         if "lin_inversion_only" in kernels:
             g_ms = kernels["lin_inversion_only"]
             fl = 2.0 * B * K * D

@@ -433,7 +433,9 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
     const int force = option(QPB_OPT_SAMPLER);
     // measured on B200 (tools/bench_configs.py): the binomial chain is sequential in O (0.0084 ms per outcome at
     // 1e5 threads) while the alias kernel scales with the shots (1.2 ms per 1e4 shots x 1e5 warps)
-    bool use_binomial = max_shots > 64L * O;
+    // (round 2c, two-pass binomial kernel: 216 outcomes x 1e4 shots 0.875 ms against 1.133 ms alias; 1296 outcomes x 1e4
+    // shots 1.04 ms against 0.495 ms alias: the crossover is near 30 shots per outcome)
+    bool use_binomial = max_shots > 32L * O;
     if (force == 1) use_binomial = false;
     if (force == 2) use_binomial = true;
     if (use_binomial) {
@@ -444,7 +446,8 @@ extern "C" int qpb_multinomial(int B, int P, int O, const double* p, int p_batch
         // group.  Measured on B200 at 36 outcomes (tools/sampler_sweep.py, profiles/r2c_sampler_groups.log): 1e5 items
         // 0.197 ms as one chain, 0.196 ms in 3 groups, 0.231 in 6 (the launch is issue-bound there: same number of
         // binomials); 12 500 items 0.097 -> 0.069 ms (chain-bound: 2 + 11 binomials per thread instead of 35)
-        int G = O / 12 < 1 ? 1 : (O / 12 > 8 ? 8 : O / 12);
+        // (216 outcomes, 1e5 items: 0.99 ms as one chain, 0.90 / 0.87 / 0.88 / 0.95 / 0.98 / 1.27 ms in 2 / 3 / 4 / 6 / 8 / 16 groups)
+        int G = O / 12 < 1 ? 1 : (O / 12 > 4 ? 4 : O / 12);
         if (option(QPB_OPT_SAMPLER_LANES) > 0) G = option(QPB_OPT_SAMPLER_LANES);
         QPB_REQUIRE(G >= 1 && G <= 64, "SAMPLER_LANES (groups per item) must be in 1..64");
         while (G > 1 && (G - 1) * ((O + G - 1) / G) >= O - 1) --G;  // the last group keeps two outcomes of its own
