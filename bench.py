@@ -31,6 +31,7 @@ global index range (weak scaling, no data-path collective).  The JSON line also 
 
 import argparse
 import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -362,6 +363,13 @@ def kernel_models():
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def quiet_gc():
+    """Collect now and keep the cyclic collector out of a timed region (a generation-2 pass over the objects the CPU
+    baseline leaves behind stalled one step of ten by 13 ms); the caller re-enables it."""
+    gc.collect()
+    gc.disable()
+
+
 class Gpu:
     """Process-wide handles of the GPU arm."""
 
@@ -730,12 +738,14 @@ def measure(gpu, cfg, steps, warmup, e2e_steps, with_cpu, cpu_seconds, with_roof
     lib.qpb_reset_launch_count()
     evs = gpu.event_pairs(steps)
     gpu.barrier()
+    quiet_gc()
     for i, (e0, e1) in enumerate(evs):
         gpu.flush.zero_()                  # evict the previous step's data from the 126 MB L2 (not timed)
         e0.record()
         wl.step(warmup + i)
         e1.record()
     gpu.barrier()
+    gc.enable()
     launches = int(lib.qpb_launch_count())
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     total_s = gpu.max_over_ranks(float(np.sum(step_ms)) / 1e3)
@@ -747,6 +757,7 @@ def measure(gpu, cfg, steps, warmup, e2e_steps, with_cpu, cpu_seconds, with_roof
     traffic0 = dict(qpar.TRAFFIC)
     times, times_full = [], []
     warm_calls = 2  # two interval objects are alive at a time: both generations of buffers exist before timing
+    quiet_gc()
     for i in range(warm_calls + e2e_steps):
         gpu.barrier()
         t0 = time.perf_counter()
@@ -761,6 +772,7 @@ def measure(gpu, cfg, steps, warmup, e2e_steps, with_cpu, cpu_seconds, with_roof
         if i >= warm_calls:
             times.append(t1 - t0)
             times_full.append(t2 - t0)
+    gc.enable()
     h2d = wl.e2e_h2d() + (qpar.TRAFFIC["h2d"] - traffic0["h2d"]) // (warm_calls + e2e_steps)
     d2h = (qpar.TRAFFIC["d2h"] - traffic0["d2h"]) // (warm_calls + e2e_steps) - B * world * 8
     e2e_s = gpu.max_over_ranks(float(np.sum(times)))
@@ -807,6 +819,7 @@ def strong_record(gpu, cfg, steps, warmup):
         step(i)
     gpu.barrier()
     evs = gpu.event_pairs(steps)
+    quiet_gc()
     for i, (e0, e1) in enumerate(evs):
         gpu.flush.zero_()
         gpu.barrier()       # ranks enter the step together, so the collective does not absorb launch skew
@@ -814,6 +827,7 @@ def strong_record(gpu, cfg, steps, warmup):
         full = step(warmup + i)
         e1.record()
     gpu.barrier()
+    gc.enable()
     each = [e0.elapsed_time(e1) for e0, e1 in evs]
     total_s = gpu.max_over_ranks(float(np.sum(each)) / 1e3)
     srt = full.cpu().numpy()
