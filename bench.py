@@ -726,6 +726,7 @@ def measure(gpu, cfg, steps, warmup, e2e_steps, with_cpu, cpu_seconds, with_roof
     world, rank = gpu.world, gpu.rank
     wl = make_workload(gpu, cfg)
     B = wl.B
+    quiet_gc()   # before the warm-up, so that the device is busy right up to the first timed step
     for i in range(warmup):
         wl.step(i)
     # a config measured after a CPU-only phase (the previous config's cpu_baseline leg) finds the SM clock at idle:
@@ -738,7 +739,6 @@ def measure(gpu, cfg, steps, warmup, e2e_steps, with_cpu, cpu_seconds, with_roof
     lib.qpb_reset_launch_count()
     evs = gpu.event_pairs(steps)
     gpu.barrier()
-    quiet_gc()
     for i, (e0, e1) in enumerate(evs):
         gpu.flush.zero_()                  # evict the previous step's data from the 126 MB L2 (not timed)
         e0.record()
@@ -815,11 +815,11 @@ def strong_record(gpu, cfg, steps, warmup):
         wl.plan.bootstrap_into(wl.bufs, wl.probs, wl.ref, wl.seed + i, lo, **wl.kw)
         return qpar.gather_sorted(wl.bufs["dist"], n_total)
 
+    quiet_gc()
     for i in range(warmup):
         step(i)
     gpu.barrier()
     evs = gpu.event_pairs(steps)
-    quiet_gc()
     for i, (e0, e1) in enumerate(evs):
         gpu.flush.zero_()
         gpu.barrier()       # ranks enter the step together, so the collective does not absorb launch skew
