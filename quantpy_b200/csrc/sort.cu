@@ -11,32 +11,7 @@ using namespace qpb;
 
 namespace qpb {
 
-// Small inputs (C1, C5 two-qubit; up to 16384 keys with QPB_OPT_NO_SAMPLE_SORT): a bitonic network in shared memory,
-// one launch of one CTA.
-constexpr int kBitonicMax = 16384;
-__global__ void __launch_bounds__(1024)
-k_sort_bitonic(int n, int m, const double* __restrict__ in, double* __restrict__ out) {
-    extern __shared__ double keys[];
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < m; i += nt) keys[i] = i < n ? in[i] : __longlong_as_double(0x7ff0000000000000ll);
-    __syncthreads();
-    for (int k = 2; k <= m; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = tid; t < (m >> 1); t += nt) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the t-th compare-exchange pair
-                const int p = i | j;
-                const double a = keys[i], b = keys[p];
-                const bool up = (i & k) == 0;
-                if ((a > b) == up) {
-                    keys[i] = b;
-                    keys[p] = a;
-                }
-            }
-            __syncthreads();
-        }
-    for (int i = tid; i < n; i += nt) out[i] = keys[i];
-}
-
+constexpr int kBitonicMax = 16384;  // k_sort_bitonic: up to 2048 keys, up to here with QPB_OPT_NO_SAMPLE_SORT
 // ------------------------------------------------------------------------------------------------
 // 2049 .. 1M keys (the 1e5 distances of BASELINE configs[1], the strong-scaling shards, configs[3] and [4]): a
 // sample sort in FOUR short launches.  The device-wide radix sort needs ten (64-bit keys: eight passes), each
@@ -69,10 +44,15 @@ __device__ __forceinline__ double ss_dec(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-// in-place ascending bitonic network over m (power of two) keys in shared memory
+// in-place ascending bitonic network over m (power of two) keys in shared memory.  Stages with partner distance
+// j >= 64 are separated by block barriers; the stages j = 32 ... 1 of every phase touch only 64 consecutive keys per
+// pair group, so each warp runs them on the chunks it owns with warp barriers alone (1024 keys: 20 block barriers
+// instead of 55).
 __device__ __forceinline__ void ss_bitonic(unsigned long long* keys, int m, int tid, int nt) {
-    for (int k = 2; k <= m; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    for (int k = 2; k <= m; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= 64; j >>= 1) {
             for (int t = tid; t < (m >> 1); t += nt) {
                 const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
                 const int p = i | j;
@@ -85,6 +65,35 @@ __device__ __forceinline__ void ss_bitonic(unsigned long long* keys, int m, int 
             }
             __syncthreads();
         }
+        // j <= 32: chunks of 64 keys (32 pairs), one warp each
+        for (int c = warp * 64; c < m; c += nw * 64) {
+            for (int jj = j; jj > 0; jj >>= 1) {
+                const int i = c + (((lane & ~(jj - 1)) << 1) | (lane & (jj - 1)));
+                const int p = i | jj;
+                if (p < m) {  // (m < 64: the upper lanes have no pair)
+                    const unsigned long long a = keys[i], b = keys[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        keys[i] = b;
+                        keys[p] = a;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Small inputs (C1, C5 two-qubit): the network in shared memory, one launch of one CTA.
+__global__ void __launch_bounds__(1024)
+k_sort_bitonic(int n, int m, const double* __restrict__ in, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned long long sm_ss[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < m; i += nt) sm_ss[i] = i < n ? ss_enc(in[i]) : ~0ull;
+    __syncthreads();
+    ss_bitonic(sm_ss, m, tid, nt);
+    for (int i = tid; i < n; i += nt) out[i] = ss_dec(sm_ss[i]);
 }
 
 // position of key i among the c keys in shared memory (ties by index): every lane reads the same word (a broadcast)
