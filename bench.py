@@ -624,10 +624,23 @@ class StateWorkload:
                        work_note="conditional-binomial sampler: bound by fixed-latency dependencies and divergence of the per-lane "
                                  "state machine (profiles/ncu_r2c_btrs.txt: FP64 pipe 12 %, 17 of 32 lanes active), no pipe roofline")
         else:
-            out.update(kernel="lin_project (k_gemm_counts_dmma + k_project_rows)", bound="issue", achieved=None, peak=None,
-                       unit=None, frac=None,
-                       work_note="the register-resident Jacobi projection dominates (profiles/ncu_r1_prof_rows8.txt: issue 61 %, "
-                                 "FP64 pipe 40 %); the DMMA inversion in front of it is reported under dmma_inversion")
+            pr = models.get("k_project_rows", {})
+            key = f"flop_per_matrix_d{plan.d}"
+            if key in pr and "lin_inversion_only" in kernels:
+                j_ms = kernels["lin_project"] - kernels["lin_inversion_only"]
+                ach = B * pr[key] / (j_ms * 1e-3) / 1e12
+                pk = gpu.fp64_peak()
+                out.update(kernel="k_project_rows (register-resident Jacobi + projection)", kernel_ms=j_ms, bound="fp64",
+                           achieved=ach, peak=pk, unit="TFLOP/s", frac=ach / pk,
+                           fp64_pipe_frac=B * pr[f"fp64_instructions_per_matrix_d{plan.d}"] * 2.0 / (j_ms * 1e-3) / 1e12 / pk,
+                           work_note=f"executed: {pr[key]} flop per matrix (ncu thread-instruction counts, "
+                                     "profiles/kernel_models.json); kernel time = lin_project - DMMA inversion, both timed alone; "
+                                     "bound by fixed-latency dependencies of the rotation chain (profiles/ncu_r2c_rows8.txt)",
+                           peak_source="qpb_fp64_fma_probe, measured in this run")
+            else:
+                out.update(kernel="lin_project (k_gemm_counts_dmma + k_project_rows)", bound="issue", achieved=None, peak=None,
+                           unit=None, frac=None,
+                           work_note="the register-resident Jacobi projection dominates; no instruction count committed for this size")
         if "lin_inversion_only" in kernels:
             g_ms = kernels["lin_inversion_only"]
             fl = 2.0 * B * K * D
