@@ -260,7 +260,9 @@ QPB_API int qpb_quantiles_host(long long n, const double* sorted_dev, int n_leve
  * unweighted POVM rows M_dev [K,D] (device, state.py:109-110), runs qpb_bootstrap_state on library-owned scratch,
  * sorts the distances into dist_sorted [B] (device, stays there: interval.py:610), interpolates the levels and
  * returns the quantiles in quantiles_host after synchronising the stream.  iters_out [B] (device) is optional.
- * n_levels may be 0 (setup only).                                                                          */
+ * n_levels may be 0 (setup only): there is then no host output and the call returns with its work QUEUED on the
+ * stream, not finished -- the multi-GPU interval queues its all-gather and merge behind it and synchronises once,
+ * in qpb_quantiles_host (the host inputs have been copied to library-owned page-locked memory by then).   */
 QPB_API int qpb_bootstrap_state_interval(const qpb_state_plan* plan, int B, int P, int O, const double* M_dev,
                                  const double* bloch_host, const double* ref_host, const int32_t* n_shots_host,
                                  uint64_t seed, uint64_t offset, int method, int physical, int init, int max_iter,

@@ -21,29 +21,41 @@
 
 namespace qpb {
 
-// Grow-only page-locked staging buffer per (device, stream); same retirement rule as scratch().
-static void* pinned_stage(cudaStream_t st, size_t bytes) {
+// Grow-only page-locked staging buffer per (device, stream); same retirement rule as scratch().  A call that
+// returns WITHOUT synchronising (qpb_bootstrap_state_interval with no levels) leaves an upload from this buffer in
+// flight, so every user waits for `uploaded` (the event recorded after the last H2D copy) before it writes to it.
+struct PinnedStage {
+    void* p = nullptr;
+    cudaEvent_t uploaded = nullptr;
+};
+static PinnedStage pinned_stage(cudaStream_t st, size_t bytes) {
     struct Buf {
         void* p = nullptr;
         size_t n = 0;
+        cudaEvent_t uploaded = nullptr;
     };
     static std::mutex mu;
     static std::map<std::pair<int, cudaStream_t>, Buf> pool;
     static std::vector<void*> retired;
     int dev = 0;
-    if (check_cuda(cudaGetDevice(&dev), "pinned_stage cudaGetDevice") != QPB_OK) return nullptr;
+    if (check_cuda(cudaGetDevice(&dev), "pinned_stage cudaGetDevice") != QPB_OK) return {};
     std::lock_guard<std::mutex> lock(mu);
     Buf& b = pool[{dev, st}];
+    if (!b.uploaded &&
+        check_cuda(cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming), "cudaEventCreate") != QPB_OK)
+        return {};
     if (b.n < bytes) {
         size_t want = bytes < 65536 ? 65536 : bytes;
         if (want < 2 * b.n) want = 2 * b.n;
         void* p = nullptr;
-        if (check_cuda(cudaHostAlloc(&p, want, cudaHostAllocDefault), "cudaHostAlloc") != QPB_OK) return nullptr;
-        if (b.p) retired.push_back(b.p);
+        if (check_cuda(cudaHostAlloc(&p, want, cudaHostAllocDefault), "cudaHostAlloc") != QPB_OK) return {};
+        if (b.p) retired.push_back(b.p);  // a copy from the old buffer may still be in flight: it is never freed
         b.p = p;
         b.n = want;
+    } else if (check_cuda(cudaEventSynchronize(b.uploaded), "pinned_stage wait") != QPB_OK) {
+        return {};  // (an event that was never recorded counts as complete)
     }
-    return b.p;
+    return {b.p, b.uploaded};
 }
 
 // out[i] = y[lo] + (y[lo + 1] - y[lo]) * (pos - lo), pos = level * (n - 1), lo = min(floor(pos), n - 2): the linear
@@ -90,11 +102,13 @@ int qpb_quantiles_host(long long n, const double* sorted_dev, int n_levels, cons
     if (rc != QPB_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t m = (size_t)n_levels;
-    double* pin = static_cast<double*>(pinned_stage(st, sizeof(double) * 2 * m));
+    const PinnedStage stage = pinned_stage(st, sizeof(double) * 2 * m);
+    double* pin = static_cast<double*>(stage.p);
     double* dev = static_cast<double*>(scratch(st, 20, sizeof(double) * 2 * m));
     if (!pin || !dev) return QPB_ERR_NOMEM;
     memcpy(pin, levels_host, sizeof(double) * m);
     QPB_CUDA(cudaMemcpyAsync(dev, pin, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    QPB_CUDA(cudaEventRecord(stage.uploaded, st));
     k_quantiles<<<(n_levels + 255) / 256, 256, 0, st>>>((long)n, sorted_dev, n_levels, dev, dev + m);
     QPB_LAUNCHED("k_quantiles");
     QPB_CUDA(cudaMemcpyAsync(pin + m, dev + m, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
@@ -118,7 +132,8 @@ int qpb_bootstrap_state_interval(const qpb_state_plan* plan, int B, int P, int O
     cudaStream_t st = (cudaStream_t)stream;
     const size_t D = (size_t)plan->D, K = (size_t)plan->K, m = (size_t)n_levels;
     const size_t n_in = D + 2 * D + m;  // Bloch vector, complex d x d centre state, levels
-    double* pin = static_cast<double*>(pinned_stage(st, sizeof(double) * (n_in + m)));
+    const PinnedStage stage = pinned_stage(st, sizeof(double) * (n_in + m));
+    double* pin = static_cast<double*>(stage.p);
     double* dev = static_cast<double*>(scratch(st, 20, sizeof(double) * (n_in + m + K)));
     // per-sample buffers the caller does not see: unsorted distances, counts, the two state buffers
     double* dist = static_cast<double*>(scratch(st, 21, sizeof(double) * (size_t)B));
@@ -129,6 +144,7 @@ int qpb_bootstrap_state_interval(const qpb_state_plan* plan, int B, int P, int O
     memcpy(pin + D, ref_host, sizeof(double) * 2 * D);
     if (m) memcpy(pin + 3 * D, levels_host, sizeof(double) * m);
     QPB_CUDA(cudaMemcpyAsync(dev, pin, sizeof(double) * n_in, cudaMemcpyHostToDevice, st));
+    QPB_CUDA(cudaEventRecord(stage.uploaded, st));
     double* bloch_dev = dev;
     double* ref_dev = dev + D;
     double* levels_dev = dev + 3 * D;
@@ -142,13 +158,14 @@ int qpb_bootstrap_state_interval(const qpb_state_plan* plan, int B, int P, int O
     if (rc != QPB_OK) return rc;
     rc = qpb_sort_f64(B, dist, dist_sorted, stream);  // interval.py:610
     if (rc != QPB_OK) return rc;
-    if (m) {
-        k_quantiles<<<(n_levels + 255) / 256, 256, 0, st>>>((long)B, dist_sorted, n_levels, levels_dev, q_dev);
-        QPB_LAUNCHED("k_quantiles");
-        QPB_CUDA(cudaMemcpyAsync(pin + n_in, q_dev, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
-    }
+    // no levels, no host output: the call returns with its work queued (the multi-GPU interval goes on to queue the
+    // all-gather and the merge behind it, and synchronises once, in qpb_quantiles_host)
+    if (!m) return QPB_OK;
+    k_quantiles<<<(n_levels + 255) / 256, 256, 0, st>>>((long)B, dist_sorted, n_levels, levels_dev, q_dev);
+    QPB_LAUNCHED("k_quantiles");
+    QPB_CUDA(cudaMemcpyAsync(pin + n_in, q_dev, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     QPB_CUDA(cudaStreamSynchronize(st));
-    if (m) memcpy(quantiles_host, pin + n_in, sizeof(double) * m);
+    memcpy(quantiles_host, pin + n_in, sizeof(double) * m);
     return QPB_OK;
 }
 
