@@ -149,6 +149,39 @@ def test_one_call_interval_equals_step_by_step_path(qp, n, povm, method, dst, B)
         qp.BootstrapStateInterval(tmg, n_points=16, method=method)([0.5, 1.2])
 
 
+def test_interval_call_without_levels_is_queued_not_lost(qp):
+    """qpb_bootstrap_state_interval with n_levels = 0 returns with its work queued (the multi-GPU interval enqueues the
+    all-gather behind it).  Calls issued back to back reuse the library's page-locked staging buffer while the
+    earlier upload may still be in flight: every call must still see ITS OWN centre state.  Reference: each call
+    followed by a synchronisation."""
+    import torch
+
+    from quantpy_b200 import engine
+
+    tmg = qp.StateTomograph(qp.Qobj(haar(2, 1)))
+    np.random.seed(3)
+    tmg.experiment(10000, "proj")
+    plan = engine.state_plan(tmg.povm_matrix, tmg.n_measurements)
+    centres = [qp.Qobj(haar(2, 50 + i)) for i in range(6)]
+    none = np.zeros(0)
+
+    def run(i, sync):
+        c = centres[i]
+        _, dist, iters = engine.bootstrap_interval(plan, c.bloch, c.matrix, 20000, 11 + i, 0, "mle", True, "lin", 300,
+                                                   1e-6, "hs", none)
+        if sync:
+            torch.cuda.synchronize()
+        return dist, iters
+
+    want = [tuple(t.cpu().numpy() for t in run(i, True)) for i in range(len(centres))]
+    got = [run(i, False) for i in range(len(centres))]          # six calls in flight on one stream
+    q = engine.quantiles_host(got[-1][0], np.array([0.0, 0.5, 1.0]))   # the one synchronisation
+    for (d0, i0), (d1, i1) in zip(want, got):
+        assert np.array_equal(d0, d1.cpu().numpy()) and np.array_equal(i0, i1.cpu().numpy())
+    assert q[0] == want[-1][0][0] and q[2] == want[-1][0][-1]
+    assert len({w[0].tobytes() for w in want}) == len(centres)   # the centres really differ
+
+
 def test_bootstrap_full_size_properties(qp):
     """BASELINE config 2 at full size (1e5 resamples): size-independent properties."""
     from quantpy_b200 import _native as nt
