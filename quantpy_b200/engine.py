@@ -208,12 +208,14 @@ def bootstrap_interval(plan, bloch, ref_matrix, n_samples, seed, offset, method,
     out = np.empty(levels.size, dtype=np.float64)
     dist = torch.empty((B,), dtype=torch.float64, device="cuda")
     iters = torch.empty((B,), dtype=torch.int32, device="cuda")
-    vp = ctypes.c_void_p
-    nt.check(plan._lib.qpb_bootstrap_state_interval(
-        plan.handle, B, plan.P, plan.O, nt.ptr(plan.M_dev), vp(bloch.ctypes.data), vp(ref.ctypes.data),
-        vp(plan.n_shots.ctypes.data), ctypes.c_uint64(seed), ctypes.c_uint64(offset), nt.METHODS[method],
+    # plain integers: the declared argtypes convert them (no ctypes objects built per call)
+    rc = plan._lib.qpb_bootstrap_state_interval(
+        plan.handle, B, plan.P, plan.O, plan.M_dev.data_ptr(), bloch.ctypes.data, ref.ctypes.data,
+        plan.n_shots.ctypes.data, int(seed), int(offset), nt.METHODS[method],
         int(bool(physical)), nt.INITS[init], int(max_iter), float(tol), nt.DIST_KINDS[dst], levels.size,
-        vp(levels.ctypes.data), vp(out.ctypes.data), nt.ptr(dist), nt.ptr(iters), nt.stream_ptr()))
+        levels.ctypes.data, out.ctypes.data, dist.data_ptr(), iters.data_ptr(), nt.stream_ptr())
+    if rc:
+        nt.check(rc)
     return out, dist, iters
 
 
