@@ -846,7 +846,7 @@ def strong_record(gpu, cfg, steps, warmup):
     srt = full.cpu().numpy()
     return {"value": n_total * steps / total_s, "unit": UNIT, "scaling": "strong", "global_resamples": n_total,
             "resamples_per_gpu": hi - lo, "n_gpus": world, "steps": steps, "ms_per_step": 1e3 * total_s / steps,
-            "ms_each": [round(t, 4) for t in each],
+            "ms_each": [round(t, 4) for t in each], "ms_per_step_median": float(np.median(each)),
             "timed_region": "sampler + lin + MLE + distance on the shard, shard sort, one all-gather, merge of the sorted "
                             "shards; CUDA events, max over ranks, L2 flushed and ranks aligned before every step",
             "sorted_ok": bool(np.all(np.diff(srt) >= 0) and len(srt) == n_total)}
