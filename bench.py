@@ -829,8 +829,12 @@ def strong_record(gpu, cfg, steps, warmup):
         return qpar.gather_sorted(wl.bufs["dist"], n_total)
 
     quiet_gc()
-    for i in range(warmup):
-        step(i)
+    full = None
+    for i in range(max(warmup, 2)):
+        # the previous step's result stays alive while the next one is produced, exactly as in the timed loop: both
+        # generations of the gathered / merged buffers exist in torch's allocator before timing (the second timed step
+        # of the 8-GPU record of round 2d paid a cudaMalloc: 1.43 ms against 0.83)
+        full = step(i)
     gpu.barrier()
     evs = gpu.event_pairs(steps)
     for i, (e0, e1) in enumerate(evs):
