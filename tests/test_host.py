@@ -260,6 +260,41 @@ def test_quantile_function_equals_scipy_interp1d():
                 ref(bad)
 
 
+def test_quantile_function_answers_the_set_up_levels_from_the_primed_result(monkeypatch):
+    """Device-resident sorted values: a call with exactly the levels of the set-up call (same bytes, same shape) is
+    answered from what that call brought back; anything else goes to qpb_quantiles_host.  Range errors come first and
+    read like interp1d's; empty and scalar level arrays pass through."""
+    from quantpy_b200 import engine, parallel
+
+    class FakeDeviceArray:
+        is_cuda = True
+
+        def numel(self):
+            return 1000
+
+    asked = []
+    monkeypatch.setattr(engine, "quantiles_host", lambda dev, levels: asked.append(levels.copy()) or levels * 2.0)
+    q = parallel.QuantileFunction(FakeDeviceArray())
+    levels = np.linspace(1e-3, 1 - 1e-3, 1000)
+    values = np.arange(1000.0)
+    q.prime(levels, values)
+    out = q(levels.copy())
+    assert np.array_equal(out, values) and not asked
+    out[0] = -1.0                                   # the caller owns what it gets
+    assert q(levels)[0] == 0.0
+    assert np.array_equal(q(list(levels)), values) and not asked          # any array-like with the same content
+    assert np.array_equal(q(levels.reshape(10, 100)), levels.reshape(10, 100) * 2.0) and len(asked) == 1  # other shape
+    other = levels.copy()
+    other[500] = np.nextafter(other[500], 1.0)
+    assert np.array_equal(q(other), other * 2.0) and len(asked) == 2
+    assert q(np.zeros(0)).shape == (0,) and q(0.5) == 1.0
+    with pytest.raises(ValueError, match="below the interpolation range"):
+        q([0.5, -1e-9, 1.5])
+    with pytest.raises(ValueError, match="above the interpolation range"):
+        q([0.5, 1 + 1e-9])
+    assert len(asked) == 4
+
+
 def test_shard_bounds_partition_any_range():
     from hypothesis import given, settings
     from hypothesis import strategies as st
